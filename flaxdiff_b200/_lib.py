@@ -1,0 +1,104 @@
+"""ctypes binding of libfdx.so (the sm_100a kernel library; C-ABI in include/fdx.h).
+
+PyTorch is only the container: tensors provide device memory (`data_ptr`) and the
+current CUDA stream.  There is no CPU or eager fallback: if the shared library is
+missing the import of any op raises, and every op requires CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libfdx.so")
+
+
+class FdxError(RuntimeError):
+    pass
+
+
+class fdx_act(ctypes.Structure):
+    _fields_ = [
+        ("ptr", ctypes.c_void_p),
+        ("n", ctypes.c_int),
+        ("h", ctypes.c_int),
+        ("w", ctypes.c_int),
+        ("c", ctypes.c_int),
+        ("pix_stride", ctypes.c_longlong),
+    ]
+
+
+class fdx_gemm_desc(ctypes.Structure):
+    _fields_ = [
+        ("mode", ctypes.c_int),
+        ("M", ctypes.c_int), ("N", ctypes.c_int), ("K", ctypes.c_int),
+        ("batch1", ctypes.c_int), ("batch2", ctypes.c_int),
+        ("A", ctypes.c_void_p), ("a_ld", ctypes.c_longlong), ("a_s1", ctypes.c_longlong), ("a_s2", ctypes.c_longlong),
+        ("B", ctypes.c_void_p), ("b_ld", ctypes.c_longlong), ("b_s1", ctypes.c_longlong), ("b_s2", ctypes.c_longlong),
+        ("D", ctypes.c_void_p), ("d_ld", ctypes.c_longlong), ("d_s1", ctypes.c_longlong), ("d_s2", ctypes.c_longlong),
+        ("d_f32", ctypes.c_int), ("d_atomic", ctypes.c_int), ("reduce_batch", ctypes.c_int),
+        ("alpha", ctypes.c_float),
+        ("bias", ctypes.c_void_p),
+        ("res", ctypes.c_void_p), ("r_ld", ctypes.c_longlong), ("r_s1", ctypes.c_longlong), ("r_s2", ctypes.c_longlong),
+    ]
+
+
+GEMM_KK, GEMM_KMN, GEMM_MNMN = 0, 1, 2
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load libfdx.so; raises FdxError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise FdxError(
+            f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C flaxdiff_b200/csrc`. flaxdiff_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.fdx_last_error.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().fdx_last_error().decode("utf-8", "replace")
+        raise FdxError(f"libfdx {what} failed with status {status}: {msg}")
+
+
+def stream_ptr() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise FdxError(f"{name}: expected a CUDA tensor (flaxdiff_b200 has no CPU path)")
+
+
+def act(t: torch.Tensor, name: str = "act") -> fdx_act:
+    """Describe an NHWC bf16 tensor (possibly a channel-slice view of a wider buffer)."""
+    _require_cuda(t, name)
+    if t.dim() != 4:
+        raise FdxError(f"{name}: expected NHWC rank-4 tensor, got {tuple(t.shape)}")
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    if sc != 1 or sh != sw * w or sn != sh * h:
+        raise FdxError(f"{name}: tensor must be pixel-contiguous NHWC (strides {t.stride()})")
+    return fdx_act(ctypes.c_void_p(t.data_ptr()), n, h, w, c, sw)
+
+
+def ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    if t is None:
+        return ctypes.c_void_p(0)
+    _require_cuda(t, "tensor")
+    return ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,427 @@
+// fdx_norm.cu -- GroupNorm(+SiLU) and RMSNorm, forward and backward, NHWC bf16.
+//
+// Replaces the XLA lowering of
+//   nn.GroupNorm(8, eps) + swish      flaxdiff/models/common.py:273-281,286-288,310-312
+//   Unet.conv_out_norm + activation   flaxdiff/models/simple_unet.py:24-30,209-210
+//   nn.RMSNorm(eps) in TransformerBlock   flaxdiff/models/attention.py:325-326
+// flax semantics kept: statistics in f32, fast variance max(0, E[x^2]-E[x]^2),
+// y = (x-mean)*rsqrt(var+eps)*scale+bias.
+//
+// HBM-bound kernels: every thread owns one 16-byte (8 x bf16) channel vector of a pixel,
+// fully coalesced; per-(image,group) partial sums are reduced with warp shuffles,
+// then shared-memory atomics, then one global atomic per block.
+#include "fdx_common.cuh"
+#include "../../include/fdx.h"
+
+namespace {
+
+constexpr int kNT = 256;
+
+struct GnGeom {
+  int vpp;      // 16-byte vectors per pixel = C/8
+  int rows;     // pixel rows per block iteration = kNT / vpp
+  int cpg;      // channels per group
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// stats[n][g] = (sum, sumsq) accumulated with atomics (buffer zeroed by the caller)
+__global__ void __launch_bounds__(kNT)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps, int HW, int C, int G,
+                float* __restrict__ stats) {
+  const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  __shared__ float sh[64];
+  if (tid < 2 * G) sh[tid] = 0.f;
+  __syncthreads();
+  if (tid < rows * vpp) {
+    const int cv = tid % vpp, r = tid / vpp;
+    const int g = (cv * 8) / cpg;
+    float s = 0.f, q = 0.f;
+    const __nv_bfloat16* base = x + (long long)n * HW * xps + cv * 8;
+    for (int p = blockIdx.x * rows + r; p < HW; p += gridDim.x * rows) {
+      float f[8];
+      load8(base + (long long)p * xps, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s += f[j]; q += f[j] * f[j]; }
+    }
+    atomicAdd(&sh[2 * g], s);
+    atomicAdd(&sh[2 * g + 1], q);
+  }
+  __syncthreads();
+  if (tid < 2 * G) atomicAdd(&stats[(long long)n * 2 * G + tid], sh[tid]);
+}
+
+__global__ void __launch_bounds__(kNT)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps, int HW, int C, int G,
+                const float* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, int silu,
+                __nv_bfloat16* __restrict__ y, long long yps) {
+  const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  if (tid >= rows * vpp) return;
+  const int cv = tid % vpp, r = tid / vpp;
+  const int g = (cv * 8) / cpg;
+  const float cnt = (float)HW * (float)cpg;
+  const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
+  const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+  const float rstd = rsqrtf(var + eps);
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float ga = gamma[cv * 8 + j];
+    a[j] = rstd * ga;
+    b[j] = beta[cv * 8 + j] - mean * rstd * ga;
+  }
+  const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
+  __nv_bfloat16* yb = y + (long long)n * HW * yps + cv * 8;
+  for (int p = blockIdx.x * rows + r; p < HW; p += gridDim.x * rows) {
+    float f[8];
+    load8(xb + (long long)p * xps, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = f[j] * a[j] + b[j];
+      f[j] = silu ? silu_f(z) : z;
+    }
+    store8(yb + (long long)p * yps, f);
+  }
+}
+
+// backward pass 1: red[n][g] = (sum dxhat, sum dxhat*xhat); dgamma/dbeta accumulated (atomics)
+__global__ void __launch_bounds__(kNT)
+gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
+                    const __nv_bfloat16* __restrict__ dy, long long dps, int HW, int C, int G,
+                    const float* __restrict__ stats, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, int silu, float* __restrict__ red,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  extern __shared__ float shm[];   // [2*G] + [2*C]
+  float* sh_red = shm;
+  float* sh_dg = shm + 2 * G;
+  float* sh_db = sh_dg + C;
+  for (int i = tid; i < 2 * G + 2 * C; i += kNT) shm[i] = 0.f;
+  __syncthreads();
+  if (tid < rows * vpp) {
+    const int cv = tid % vpp, r = tid / vpp;
+    const int g = (cv * 8) / cpg;
+    const float cnt = (float)HW * (float)cpg;
+    const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
+    const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+    const float rstd = rsqrtf(var + eps);
+    float ga[8], be[8], dg[8], db[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ga[j] = gamma[cv * 8 + j]; be[j] = beta[cv * 8 + j]; dg[j] = 0.f; db[j] = 0.f;
+    }
+    float s1 = 0.f, s2 = 0.f;
+    const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
+    const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
+    for (int p = blockIdx.x * rows + r; p < HW; p += gridDim.x * rows) {
+      float f[8], d[8];
+      load8(xb + (long long)p * xps, f);
+      load8(db_ + (long long)p * dps, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (f[j] - mean) * rstd;
+        float dz = d[j];
+        if (silu) {
+          const float z = xh * ga[j] + be[j];
+          const float sg = 1.f / (1.f + __expf(-z));
+          dz *= sg * (1.f + z * (1.f - sg));
+        }
+        dg[j] += dz * xh;
+        db[j] += dz;
+        const float dxh = dz * ga[j];
+        s1 += dxh;
+        s2 += dxh * xh;
+      }
+    }
+    atomicAdd(&sh_red[2 * g], s1);
+    atomicAdd(&sh_red[2 * g + 1], s2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh_dg[cv * 8 + j], dg[j]);
+      atomicAdd(&sh_db[cv * 8 + j], db[j]);
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * G) atomicAdd(&red[(long long)n * 2 * G + tid], sh_red[tid]);
+  for (int c = tid; c < C; c += kNT) {
+    atomicAdd(&dgamma[c], sh_dg[c]);
+    atomicAdd(&dbeta[c], sh_db[c]);
+  }
+}
+
+// backward pass 2: dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat))   (+= if accumulate)
+__global__ void __launch_bounds__(kNT)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
+                    const __nv_bfloat16* __restrict__ dy, long long dps, int HW, int C, int G,
+                    const float* __restrict__ stats, const float* __restrict__ red,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                    int silu, __nv_bfloat16* __restrict__ dx, long long dxps, int accumulate) {
+  const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  if (tid >= rows * vpp) return;
+  const int cv = tid % vpp, r = tid / vpp;
+  const int g = (cv * 8) / cpg;
+  const float cnt = (float)HW * (float)cpg;
+  const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
+  const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+  const float rstd = rsqrtf(var + eps);
+  const float m1 = red[(long long)n * 2 * G + 2 * g] / cnt;
+  const float m2 = red[(long long)n * 2 * G + 2 * g + 1] / cnt;
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ga[j] = gamma[cv * 8 + j]; be[j] = beta[cv * 8 + j]; }
+  const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
+  const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
+  __nv_bfloat16* ob = dx + (long long)n * HW * dxps + cv * 8;
+  for (int p = blockIdx.x * rows + r; p < HW; p += gridDim.x * rows) {
+    float f[8], d[8], o[8];
+    load8(xb + (long long)p * xps, f);
+    load8(db_ + (long long)p * dps, d);
+    if (accumulate) load8(ob + (long long)p * dxps, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (f[j] - mean) * rstd;
+      float dz = d[j];
+      if (silu) {
+        const float z = xh * ga[j] + be[j];
+        const float sg = 1.f / (1.f + __expf(-z));
+        dz *= sg * (1.f + z * (1.f - sg));
+      }
+      const float v = rstd * (dz * ga[j] - m1 - xh * m2);
+      o[j] = accumulate ? o[j] + v : v;
+    }
+    store8(ob + (long long)p * dxps, o);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// RMSNorm over channels, one warp per pixel.
+// ---------------------------------------------------------------------------
+template <int VPL>   // 16-byte vectors per lane: C = 256 * VPL
+__global__ void __launch_bounds__(256)
+rms_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long xps, long long npix, int C,
+               const float* __restrict__ scale, float eps, __nv_bfloat16* __restrict__ y,
+               long long yps) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * 8;
+  for (long long p = wid; p < npix; p += nw) {
+    float f[VPL][8];
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      load8(x + p * xps + (v * 32 + lane) * 8, f[v]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q += f[v][j] * f[v][j];
+    }
+    q = warp_sum(q);
+    const float r = rsqrtf(q / (float)C + eps);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = f[v][j] * r * scale[(v * 32 + lane) * 8 + j];
+      store8(y + p * yps + (v * 32 + lane) * 8, o);
+    }
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256)
+rms_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
+               const __nv_bfloat16* __restrict__ dy, long long dps, long long npix, int C,
+               const float* __restrict__ scale, float eps, __nv_bfloat16* __restrict__ dx,
+               long long dxps, int accumulate, float* __restrict__ dscale) {
+  extern __shared__ float sh_ds[];   // [C]
+  for (int i = threadIdx.x; i < C; i += 256) sh_ds[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * 8;
+  float ds[VPL][8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ds[v][j] = 0.f;
+  for (long long p = wid; p < npix; p += nw) {
+    float f[VPL][8], d[VPL][8];
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      load8(x + p * xps + (v * 32 + lane) * 8, f[v]);
+      load8(dy + p * dps + (v * 32 + lane) * 8, d[v]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q += f[v][j] * f[v][j];
+    }
+    q = warp_sum(q);
+    const float r = rsqrtf(q / (float)C + eps);
+    float m = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = f[v][j] * r;
+        ds[v][j] += d[v][j] * xh;
+        d[v][j] *= scale[(v * 32 + lane) * 8 + j];   // g = dy * scale
+        m += d[v][j] * xh;
+      }
+    m = warp_sum(m) / (float)C;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      float o[8];
+      if (accumulate) load8(dx + p * dxps + (v * 32 + lane) * 8, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float val = r * (d[v][j] - f[v][j] * r * m);
+        o[j] = accumulate ? o[j] + val : val;
+      }
+      store8(dx + p * dxps + (v * 32 + lane) * 8, o);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sh_ds[(v * 32 + lane) * 8 + j], ds[v][j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(&dscale[i], sh_ds[i]);
+}
+
+int gn_check(const fdx_act* x, int groups, const char* what) {
+  FDX_REQUIRE(x && x->ptr, "%s: null tensor", what);
+  FDX_REQUIRE(groups > 0 && groups <= 32 && x->c % groups == 0, "%s: bad group count %d", what, groups);
+  FDX_REQUIRE((x->c / groups) % 8 == 0, "%s: channels per group (%d) must be a multiple of 8", what,
+              x->c / groups);
+  FDX_REQUIRE(x->c / 8 <= kNT, "%s: C=%d too large", what, x->c);
+  FDX_REQUIRE(x->pix_stride % 8 == 0, "%s: pix_stride must be a multiple of 8", what);
+  return FDX_OK;
+}
+
+dim3 gn_grid(const fdx_act* x) {
+  const int HW = x->h * x->w;
+  const int rows = kNT / (x->c / 8);
+  int bx = (HW + rows - 1) / rows;
+  // enough blocks to fill the machine, but keep >= ~8 pixels per thread row
+  int target = (4 * 148 + x->n - 1) / x->n;
+  if (target < 1) target = 1;
+  if (bx > target) bx = target;
+  return dim3(bx, x->n);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdx_groupnorm_stats(const fdx_act* x, int groups, float* stats, void* stream) {
+  int s = gn_check(x, groups, "groupnorm_stats");
+  if (s != FDX_OK) return s;
+  cudaStream_t st = (cudaStream_t)stream;
+  FDX_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * x->n, st));
+  gn_stats_kernel<<<gn_grid(x), kNT, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pix_stride,
+                                              x->h * x->w, x->c, groups, stats);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const float* gamma,
+                        const float* beta, float eps, int silu, const fdx_act* y, void* stream) {
+  int s = gn_check(x, groups, "groupnorm_apply");
+  if (s != FDX_OK) return s;
+  FDX_REQUIRE(y && y->ptr && y->n == x->n && y->h == x->h && y->w == x->w && y->c == x->c,
+              "groupnorm_apply: output shape mismatch");
+  gn_apply_kernel<<<gn_grid(x), kNT, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, x->h * x->w, x->c, groups, stats, gamma, beta,
+      eps, silu, (__nv_bfloat16*)y->ptr, y->pix_stride);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
+                      const float* gamma, const float* beta, float eps, int silu, float* red,
+                      float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
+                      void* stream) {
+  int s = gn_check(x, groups, "groupnorm_bwd");
+  if (s != FDX_OK) return s;
+  FDX_REQUIRE(dy && dy->ptr && dx && dx->ptr, "groupnorm_bwd: null tensor");
+  FDX_REQUIRE(dy->c == x->c && dx->c == x->c && dy->n == x->n && dx->n == x->n &&
+                  dy->h == x->h && dy->w == x->w && dx->h == x->h && dx->w == x->w,
+              "groupnorm_bwd: shape mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  FDX_CUDA(cudaMemsetAsync(red, 0, sizeof(float) * 2 * groups * x->n, st));
+  const size_t shm = sizeof(float) * (2 * groups + 2 * x->c);
+  gn_bwd_stats_kernel<<<gn_grid(x), kNT, shm, st>>>(
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride,
+      x->h * x->w, x->c, groups, stats, gamma, beta, eps, silu, red, dgamma, dbeta);
+  FDX_LAUNCH_CHECK();
+  gn_bwd_apply_kernel<<<gn_grid(x), kNT, 0, st>>>(
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride,
+      x->h * x->w, x->c, groups, stats, red, gamma, beta, eps, silu, (__nv_bfloat16*)dx->ptr,
+      dx->pix_stride, accumulate);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_rmsnorm_fwd(const fdx_act* x, const float* scale, float eps, const fdx_act* y,
+                    void* stream) {
+  FDX_REQUIRE(x && x->ptr && y && y->ptr, "rmsnorm_fwd: null tensor");
+  FDX_REQUIRE(x->c % 256 == 0 && x->c <= 1024, "rmsnorm_fwd: C=%d must be 256/512/768/1024", x->c);
+  const long long npix = (long long)x->n * x->h * x->w;
+  int grid = (int)((npix + 7) / 8);
+  if (grid > 148 * 8) grid = 148 * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+#define RMS_F(V)                                                                               \
+  rms_fwd_kernel<V><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pix_stride, npix,  \
+                                          x->c, scale, eps, (__nv_bfloat16*)y->ptr, y->pix_stride)
+  switch (x->c / 256) {
+    case 1: RMS_F(1); break;
+    case 2: RMS_F(2); break;
+    case 3: RMS_F(3); break;
+    default: RMS_F(4); break;
+  }
+#undef RMS_F
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_rmsnorm_bwd(const fdx_act* x, const fdx_act* dy, const float* scale, float eps,
+                    const fdx_act* dx, int accumulate, float* dscale, void* stream) {
+  FDX_REQUIRE(x && x->ptr && dy && dy->ptr && dx && dx->ptr, "rmsnorm_bwd: null tensor");
+  FDX_REQUIRE(x->c % 256 == 0 && x->c <= 1024, "rmsnorm_bwd: C=%d must be 256/512/768/1024", x->c);
+  const long long npix = (long long)x->n * x->h * x->w;
+  int grid = (int)((npix + 7) / 8);
+  if (grid > 148 * 4) grid = 148 * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t shm = sizeof(float) * x->c;
+#define RMS_B(V)                                                                                 \
+  rms_bwd_kernel<V><<<grid, 256, shm, st>>>(                                                     \
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, \
+      npix, x->c, scale, eps, (__nv_bfloat16*)dx->ptr, dx->pix_stride, accumulate, dscale)
+  switch (x->c / 256) {
+    case 1: RMS_B(1); break;
+    case 2: RMS_B(2); break;
+    case 3: RMS_B(3); break;
+    default: RMS_B(4); break;
+  }
+#undef RMS_B
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+}  // extern "C"

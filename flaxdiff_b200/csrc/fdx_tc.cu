@@ -1,0 +1,486 @@
+// fdx_tc.cu -- the tcgen05 / TMA / TMEM "tap-GEMM" engine for sm_100a.
+//
+// Replaces what the reference delegates to XLA for every dense contraction on the
+// UNet hot path: flax nn.Conv 3x3 / 1x1 (flaxdiff/models/common.py:166-172,
+// 237-244, 324-333), nn.DenseGeneral projections (models/attention.py:132-154)
+// and the QK^T / PV products of nn.dot_product_attention (attention.py:170-174),
+// forward and backward.
+//
+// Design (one CTA per SM, persistent over output tiles, 6 warps):
+//   warp 0      TMA producer: per K-chunk one 128B-swizzled A box (64 channels x
+//               128 pixels, shifted by the tap offset; out-of-image = zero fill
+//               = SAME padding) and the matching B box, into a ring of stages.
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN,
+//               K=16, bf16 -> f32) into a double-buffered TMEM accumulator and
+//               tcgen05.commit's the stage back to the producer.
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (one pixel row per thread),
+//               fuse bias + per-image timestep vector + residual, store bf16/f32
+//               (or f32 atomics for the split-K weight gradient).
+#include "fdx_tc.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBK = 64;                 // K elements (or K rows) per pipeline stage
+constexpr int kABytes = 128 * kBK * 2;  // 16 KB per stage for A in every mode
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = (BN == 64) ? 8 : (BN == 128) ? 6 : 4;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+struct TcDev {
+  int mode;
+  int TW, TH, TN;        // pixel box of one A tile (128 pixels for K-major A, 64 for MN-major A)
+  int nxb, nyb, nnb;     // pixel blocks along x, y, n
+  int W, H, N;
+  int es;
+  int ntaps;
+  int tap_dx[9], tap_dy[9], tap_b[9];
+  int kchunks;           // K chunks per tap (TC_KK/TC_KMN)
+  int K;
+  int M;                 // TC_MNMN valid rows
+  int mblks;             // TC_MNMN: row blocks of 128
+  int Ncols, nblks;      // column blocks of BN
+  int b_batched;
+  int mn_batched;        // TC_MNMN: reduce over x blocks only, (y, n) blocks are batch
+  int splits;
+  int ntiles;
+  // epilogue
+  void* out;
+  int out_f32, out_atomic;
+  long long os_x, os_y, os_n, os_tap, os_m;
+  float alpha;
+  const float* bias;
+  const float* rowvec;
+  const void* res;
+  long long rs_x, rs_y, rs_n;
+};
+
+// TC_MNMN tile decode: tile -> (batch block bz, split, nt, mb, tap) and the K range [pb0, pb1)
+struct MnTile {
+  int bz, sp, nt, mb, t, pb0, pb1;
+};
+__device__ __forceinline__ MnTile decode_mn(const TcDev& p, int tile) {
+  MnTile m;
+  int r = tile;
+  const int nbz = p.mn_batched ? p.nyb * p.nnb : 1;
+  m.bz = r % nbz; r /= nbz;
+  m.sp = r % p.splits; r /= p.splits;
+  m.nt = r % p.nblks;  r /= p.nblks;
+  m.mb = r % p.mblks;  r /= p.mblks;
+  m.t = r;
+  const long long kblocks = p.mn_batched ? p.nxb : (long long)p.nxb * p.nyb * p.nnb;
+  m.pb0 = (int)((kblocks * m.sp) / p.splits);
+  m.pb1 = (int)((kblocks * (m.sp + 1)) / p.splits);
+  return m;
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+              const TcDev p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  constexpr bool A_MN = (MODE == TC_MNMN);
+  constexpr bool B_MN = (MODE != TC_KK);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* full = bars;            // [S]
+  uint64_t* empty = bars + S;       // [S]
+  uint64_t* tfull = bars + 2 * S;   // [2]
+  uint64_t* tempty = bars + 2 * S + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 4);
+    mbar_init(&tempty[1], 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- tile decode helpers ------------------------------------------------
+  // TC_KK / TC_KMN : tile -> (nt, xb, yb, nb);  nk = ntaps * kchunks
+  // TC_MNMN        : tile -> (split, nt, mb, tap); nk = pixel blocks of this split
+
+  if (warp == 0) {
+    // =========================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        if constexpr (!A_MN) {
+          const int nt = tile % p.nblks;
+          const int mt = tile / p.nblks;
+          const int xb = mt % p.nxb;
+          const int yb = (mt / p.nxb) % p.nyb;
+          const int nb = mt / (p.nxb * p.nyb);
+          const int x0 = xb * p.TW * p.es, y0 = yb * p.TH * p.es, n0 = nb * p.TN;
+          const int zb1 = p.b_batched ? yb : 0, zb2 = p.b_batched ? nb : 0;
+          for (int t = 0; t < p.ntaps; ++t) {
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::kStageBytes;
+              uint8_t* sb = sa + kABytes;
+              mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+              tma_load_4d(sa, &mapA, &full[stage], kc * kBK, x0 + p.tap_dx[t], y0 + p.tap_dy[t],
+                          n0);
+              if constexpr (!B_MN) {
+                // B K-major: box (64 k, BN rows); tap selects z1 (or batched z1/z2)
+                tma_load_4d(sb, &mapB, &full[stage], kc * kBK, nt * BN,
+                            p.b_batched ? zb1 : p.tap_b[t], zb2);
+              } else {
+                // B MN-major: BN/64 boxes of (64 n, 64 k rows)
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_4d(sb + j * (kBK * 128), &mapB, &full[stage], nt * BN + j * 64,
+                              p.tap_b[t] + kc * kBK, zb1, zb2);
+              }
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
+          const MnTile mt_ = decode_mn(p, tile);
+          const int nt = mt_.nt, mb = mt_.mb, t = mt_.t;
+          for (int pb = mt_.pb0; pb < mt_.pb1; ++pb) {
+            int xb, yb, nb;
+            if (p.mn_batched) {
+              xb = pb; yb = mt_.bz % p.nyb; nb = mt_.bz / p.nyb;
+            } else {
+              xb = pb % p.nxb; yb = (pb / p.nxb) % p.nyb; nb = pb / (p.nxb * p.nyb);
+            }
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+            const int ax = xb * p.TW * p.es + p.tap_dx[t], ay = yb * p.TH * p.es + p.tap_dy[t];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tma_load_4d(sa + j * (kBK * 128), &mapA, &full[stage], mb * 128 + j * 64, ax, ay,
+                          nb * p.TN);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sb + j * (kBK * 128), &mapB, &full[stage], nt * BN + j * 64, xb * p.TW,
+                          yb * p.TH, nb * p.TN);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int nk;
+        if constexpr (!A_MN) {
+          nk = p.ntaps * p.kchunks;
+        } else {
+          const MnTile mt_ = decode_mn(p, tile);
+          nk = mt_.pb1 - mt_.pb0;
+        }
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int i = 0; i < nk; ++i) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // K-major: advance 16 elements (32 B) inside the 128B swizzle row; SBO = 8 rows.
+            // MN-major: advance 16 k-rows (2048 B); LBO = next 64-wide block, SBO = 8 rows.
+            const uint64_t da = A_MN ? umma_desc_sw128(sa + k * 2048, kBK * 128, 1024)
+                                     : umma_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, kBK * 128, 1024)
+                                     : umma_desc_sw128(sb + k * 32, 16, 1024);
+            umma_f16(d_tmem, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);   // frees the smem stage when these MMAs retire
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        if (nk == 0) {
+          // nothing accumulated for this tile: epilogue must not read garbage
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ============================= epilogue =================================
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;       // accumulator row owned by this thread
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int nt;
+      bool valid;
+      long long obase, rbase = 0;
+      int img = 0;
+      bool has_acc = true;
+      if constexpr (!A_MN) {
+        nt = tile % p.nblks;
+        const int mt = tile / p.nblks;
+        const int xb = mt % p.nxb;
+        const int yb = (mt / p.nxb) % p.nyb;
+        const int nb = mt / (p.nxb * p.nyb);
+        const int tx = row % p.TW, ty = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
+        const int x = xb * p.TW + tx, y = yb * p.TH + ty, n = nb * p.TN + tn;
+        valid = (x < p.W) && (y < p.H) && (n < p.N);
+        img = n;
+        obase = (long long)n * p.os_n + (long long)y * p.os_y + (long long)x * p.os_x;
+        if (p.res) rbase = (long long)n * p.rs_n + (long long)y * p.rs_y + (long long)x * p.rs_x;
+      } else {
+        const MnTile mt_ = decode_mn(p, tile);
+        nt = mt_.nt;
+        const int m = mt_.mb * 128 + row;
+        valid = m < p.M;
+        obase = (long long)p.tap_b[mt_.t] * p.os_tap + (long long)m * p.os_m;
+        if (p.mn_batched)
+          obase += (long long)(mt_.bz % p.nyb) * p.os_y + (long long)(mt_.bz / p.nyb) * p.os_n;
+        has_acc = (mt_.pb1 - mt_.pb0) > 0;
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + c0, v);
+        tmem_ld_wait();
+        const int col0 = nt * BN + c0;
+        if (valid && has_acc && col0 < p.Ncols) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.rowvec) {
+            const float* rv = p.rowvec + (long long)img * p.Ncols + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(rv + j);
+          }
+          if (p.res) {
+            const uint4* rp =
+                reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res) + rbase + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = rp[j];
+              float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+                     d = unpack_bf16x2(u.w);
+              f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+              f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+            }
+          }
+          if (p.out_atomic) {
+            float* op = static_cast<float*>(p.out) + obase + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(op + j, f[j]);
+          } else if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + obase + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* op =
+                reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + obase + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              op[j] = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int MODE>
+int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d, cudaStream_t stream) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FDX_CUDA(cudaFuncSetAttribute(fdx_tc_kernel<BN, MODE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  int grid = fdx_num_sms();
+  if (grid <= 0) return FDX_ERR_NO_DEVICE;
+  if (d.ntiles < grid) grid = d.ntiles;
+  fdx_tc_kernel<BN, MODE><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA, mB, d);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+template <int MODE>
+int launch_mode(int BN, const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d,
+                cudaStream_t stream) {
+  switch (BN) {
+    case 64: return launch_cfg<64, MODE>(mA, mB, d, stream);
+    case 128: return launch_cfg<128, MODE>(mA, mB, d, stream);
+    case 256: return launch_cfg<256, MODE>(mA, mB, d, stream);
+  }
+  fdx_set_error("tc: unsupported BN %d", BN);
+  return FDX_ERR_UNSUPPORTED;
+}
+
+int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+}  // namespace
+
+int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
+  FDX_REQUIRE(L.mode >= TC_KK && L.mode <= TC_MNMN, "tc: bad mode %d", L.mode);
+  FDX_REQUIRE(L.ntaps >= 1 && L.ntaps <= 9, "tc: bad ntaps %d", L.ntaps);
+  FDX_REQUIRE(L.es == 1 || L.es == 2, "tc: bad element stride %d", L.es);
+  FDX_REQUIRE(L.Ncols > 0 && L.Ncols % 64 == 0, "tc: Ncols=%d must be a multiple of 64", L.Ncols);
+  FDX_REQUIRE(L.A.strides[0] == 1 && L.B.strides[0] == 1, "tc: innermost strides must be 1");
+
+  TcDev d{};
+  d.mode = L.mode;
+  d.W = L.W; d.H = L.H; d.N = L.N; d.es = L.es; d.ntaps = L.ntaps;
+  for (int i = 0; i < 9; ++i) { d.tap_dx[i] = L.tap_dx[i]; d.tap_dy[i] = L.tap_dy[i]; d.tap_b[i] = L.tap_b[i]; }
+  d.K = L.K; d.M = L.M; d.Ncols = L.Ncols; d.b_batched = L.b_batched; d.mn_batched = L.mn_batched;
+  d.out = L.out; d.out_f32 = L.out_f32; d.out_atomic = L.out_atomic;
+  d.os_x = L.os_x; d.os_y = L.os_y; d.os_n = L.os_n; d.os_tap = L.os_tap; d.os_m = L.os_m;
+  d.alpha = L.alpha; d.bias = L.bias; d.rowvec = L.rowvec; d.res = L.res;
+  d.rs_x = L.rs_x; d.rs_y = L.rs_y; d.rs_n = L.rs_n;
+
+  // ---- column tile --------------------------------------------------------
+  int BN = (L.Ncols % 256 == 0) ? 256 : (L.Ncols % 128 == 0) ? 128 : 64;
+  // keep enough tiles in flight for 148 SMs: shrink BN if the grid would be tiny
+  const int rows_per_tile = (L.mode == TC_MNMN) ? 64 : 128;
+  // ---- pixel box ----------------------------------------------------------
+  int TW, TH, TN;
+  if (!L.gemm_like) {
+    // conv: a 16 x 8 (or 16 x 4) pixel patch; small images pack several per tile
+    TW = pow2_floor(L.W < 16 ? L.W : 16);
+    int rem = rows_per_tile / TW;
+    TH = pow2_floor(L.H < rem ? L.H : rem);
+    TN = rem / TH;
+  } else {
+    // GEMM: rows along x only; (y, n) are batch coordinates. A box taller than the
+    // matrix is fine: TMA zero-fills and the epilogue predicates on x < W.
+    TW = rows_per_tile;
+    TH = 1;
+    TN = 1;
+  }
+  d.TW = TW; d.TH = TH; d.TN = TN;
+  d.nxb = (L.W + TW - 1) / TW;
+  d.nyb = (L.H + TH - 1) / TH;
+  d.nnb = (L.N + TN - 1) / TN;
+  const long long pix_blocks = (long long)d.nxb * d.nyb * d.nnb;
+
+  if (L.mode != TC_MNMN) {
+    while (BN > 64 && pix_blocks * (L.Ncols / BN) < 2LL * fdx_num_sms()) BN /= 2;
+    d.nblks = L.Ncols / BN;
+    d.kchunks = (L.K + kBK - 1) / kBK;
+    d.ntiles = (int)(pix_blocks * d.nblks);
+    d.splits = 1;
+    d.mblks = 1;
+    FDX_REQUIRE(!L.res || !L.out_atomic, "tc: residual with atomic output unsupported");
+  } else {
+    if (BN > 128) BN = 128;   // 2 A blocks + BN/64 B blocks of 8 KB per stage
+    d.nblks = L.Ncols / BN;
+    d.mblks = (L.M + 127) / 128;
+    d.kchunks = 0;
+    long long base_tiles = (long long)L.ntaps * d.mblks * d.nblks;
+    const long long kblocks = L.mn_batched ? d.nxb : pix_blocks;
+    const long long nbz = L.mn_batched ? (long long)d.nyb * d.nnb : 1;
+    int splits = L.splits;
+    if (splits <= 0) {
+      const int sms = fdx_num_sms();
+      splits = (int)((2LL * sms + base_tiles * nbz - 1) / (base_tiles * nbz));
+      if (splits < 1) splits = 1;
+    }
+    if (splits > kblocks) splits = (int)kblocks;
+    FDX_REQUIRE(splits == 1 || L.out_atomic, "tc: split-K needs atomic output");
+    d.splits = splits;
+    d.ntiles = (int)(base_tiles * splits * nbz);
+  }
+
+  // ---- tensor maps ----------------------------------------------------------
+  CUtensorMap mA, mB;
+  {
+    uint64_t dims[4], str[3];
+    for (int i = 0; i < 4; ++i) dims[i] = L.A.dims[i];
+    for (int i = 1; i < 4; ++i) str[i - 1] = L.A.strides[i] * 2;
+    uint32_t box[4] = {64, (uint32_t)(TW * L.es), (uint32_t)(TH * L.es), (uint32_t)TN};
+    uint32_t est[4] = {1, (uint32_t)L.es, (uint32_t)L.es, 1};
+    int s = fdx_make_tmap_bf16(&mA, L.A.ptr, 4, dims, str, box, est, 1);
+    if (s != FDX_OK) return s;
+  }
+  {
+    uint64_t dims[4], str[3];
+    for (int i = 0; i < 4; ++i) dims[i] = L.B.dims[i];
+    for (int i = 1; i < 4; ++i) str[i - 1] = L.B.strides[i] * 2;
+    uint32_t box[4];
+    uint32_t est[4] = {1, 1, 1, 1};
+    if (L.mode == TC_KK) {
+      box[0] = 64; box[1] = (uint32_t)BN; box[2] = 1; box[3] = 1;
+    } else if (L.mode == TC_KMN) {
+      box[0] = 64; box[1] = 64; box[2] = 1; box[3] = 1;
+    } else {
+      box[0] = 64; box[1] = (uint32_t)TW; box[2] = (uint32_t)TH; box[3] = (uint32_t)TN;
+    }
+    int s = fdx_make_tmap_bf16(&mB, L.B.ptr, 4, dims, str, box, est, 1);
+    if (s != FDX_OK) return s;
+  }
+
+  switch (L.mode) {
+    case TC_KK: return launch_mode<TC_KK>(BN, mA, mB, d, stream);
+    case TC_KMN: return launch_mode<TC_KMN>(BN, mA, mB, d, stream);
+    default: return launch_mode<TC_MNMN>(BN, mA, mB, d, stream);
+  }
+}

@@ -1,0 +1,55 @@
+// fdx_tc.cuh -- launch descriptor of the tcgen05 "tap-GEMM" engine (fdx_tc.cu).
+//
+// One persistent, warp-specialised kernel computes
+//     D[m, n] = alpha * sum_{tap t} sum_{k} A_t[m, k] * B_t[n, k]   (+ epilogue)
+// where the A operand is a 4-D NHWC (or strided 2-D / batched) bf16 tensor read
+// through TMA with a per-tap spatial shift (zero fill outside the image = SAME
+// padding), and B is either K-major ([n][k], k contiguous) or MN-major
+// ([k][n], n contiguous).  This single engine is the 3x3 conv forward, dgrad,
+// wgrad, 1x1 conv, dense layer and the attention contractions.
+#pragma once
+#include "fdx_common.cuh"
+
+struct TcOperand {
+  const void* ptr;        // bf16
+  uint64_t dims[4];       // innermost first: (c, x, y, n)
+  uint64_t strides[4];    // in ELEMENTS; strides[0] must be 1
+};
+
+enum TcMode {
+  TC_KK = 0,     // A K-major (rows = pixels, k = channels), B K-major
+  TC_KMN = 1,    // A K-major, B MN-major (n contiguous, k = rows)
+  TC_MNMN = 2,   // A MN-major (m = channels, k = pixels), B MN-major  (wgrad-type)
+};
+
+struct TcLaunch {
+  int mode;
+  TcOperand A, B;
+  // logical output pixel space (x, y, n) for TC_KK/TC_KMN; reduction pixel space for TC_MNMN
+  int W, H, N;
+  int es;                 // element stride of the A read (1, or 2 for stride-2 conv)
+  int ntaps;              // 1..9
+  int tap_dx[9], tap_dy[9];   // A spatial offset of tap t (already includes -pad)
+  int tap_b[9];           // TC_KK: B z1 coordinate of tap t; TC_KMN: B row offset of tap t (elements of k);
+                          // TC_MNMN: output slab index of tap t
+  int K;                  // channels per tap (TC_KK/TC_KMN); ignored for TC_MNMN
+  int M;                  // TC_MNMN only: valid rows (channels of A)
+  int Ncols;              // total output columns
+  int b_batched;          // B z1/z2 coordinates follow the tile's (y, n) block (batched GEMM)
+  int mn_batched;         // TC_MNMN: reduce over x only; (y, n) index the batch (os_y/os_n used)
+  int gemm_like;          // rows along x only (no 2-D pixel patch)
+  // epilogue
+  void* out;              // bf16 or f32
+  int out_f32;
+  int out_atomic;         // f32 atomicAdd (TC_MNMN split-K)
+  long long os_x, os_y, os_n;   // output element offsets per pixel coordinate (TC_KK/TC_KMN)
+  long long os_tap, os_m;       // TC_MNMN: out[tap_b*os_tap + m*os_m + n]
+  float alpha;
+  const float* bias;      // [Ncols] or null
+  const float* rowvec;    // [N][Ncols] per-image vector (timestep embedding add) or null
+  const void* res;        // bf16 residual / accumulate source or null
+  long long rs_x, rs_y, rs_n;
+  int splits;             // TC_MNMN: split-K factor (0 = auto)
+};
+
+int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream);
