@@ -184,7 +184,7 @@ int fdx_gemm(const fdx_gemm_desc* g, void* stream) {
   FDX_REQUIRE(g && g->A && g->B && g->D, "gemm: null pointer");
   FDX_REQUIRE(g->mode >= 0 && g->mode <= 2, "gemm: bad mode");
   FDX_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "gemm: bad dims");
-  FDX_REQUIRE(g->N % 64 == 0, "gemm: N=%d must be a multiple of 64", g->N);
+  FDX_REQUIRE(g->N % 32 == 0, "gemm: N=%d must be a multiple of 32", g->N);
   const int b1 = g->batch1 > 0 ? g->batch1 : 1, b2 = g->batch2 > 0 ? g->batch2 : 1;
   TcLaunch L{};
   L.mode = g->mode;

@@ -1,0 +1,259 @@
+// fdx_conv_direct.cu -- the two 3-channel 3x3 convolutions of the UNet on CUDA cores.
+//
+//   conv_in   Cin=3  -> 64   flaxdiff/models/simple_unet.py:47-54   (K = 27: too thin for an MMA tile)
+//   conv_out  64 -> Cout=3   flaxdiff/models/simple_unet.py:212-221 (N = 3)
+// Both are HBM-bound (0.23 GFLOP/img at 256^2 against 17 MB/img of activation traffic), so
+// they run as direct convolutions: weights in shared memory, one 16-byte channel vector
+// per thread, f32 accumulation. Forward and all gradients.
+#include "fdx_common.cuh"
+#include "../../include/fdx.h"
+
+namespace {
+
+// ---- conv_in forward: x bf16 [N,H,W,3] dense, w f32 [9][3][Cout], y bf16 act ------------
+__global__ void __launch_bounds__(256)
+cin3_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                const float* __restrict__ bias, int N, int H, int W, int Cout,
+                __nv_bfloat16* __restrict__ y, long long yps) {
+  extern __shared__ float sw[];   // [27][Cout] + [Cout]
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int vpp = Cout >> 3;
+  const long long total = (long long)N * H * W * vpp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vpp);
+    long long p = i / vpp;
+    const int px = (int)(p % W);
+    const int py = (int)((p / W) % H);
+    const int n = (int)(p / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sw[27 * Cout + cv * 8 + j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = py + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = px + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        const __nv_bfloat16* xp = x + ((long long)(n * H + iy) * W + ix) * 3;
+        const float v0 = __bfloat162float(xp[0]), v1 = __bfloat162float(xp[1]),
+                    v2 = __bfloat162float(xp[2]);
+        const float* wp = sw + ((ky * 3 + kx) * 3) * Cout + cv * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          acc[j] += v0 * wp[j] + v1 * wp[Cout + j] + v2 * wp[2 * Cout + j];
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(y + p * yps + cv * 8) = o;
+  }
+}
+
+// ---- conv_in wgrad: dW[t][cs][co] += sum_p x[p+d(t)][cs] * dY[p][co]; db[co] += sum_p dY ----
+__global__ void __launch_bounds__(576)
+cin3_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                  long long dps, int N, int H, int W, int Cout, float* __restrict__ dw,
+                  float* __restrict__ db) {
+  // blockDim = 9 * Cout (Cout == 64); thread = (tap, co)
+  const int t = threadIdx.x / Cout, co = threadIdx.x % Cout;
+  const int ky = t / 3, kx = t % 3;
+  const long long npix = (long long)N * H * W;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per, p1 = (p0 + per < npix) ? p0 + per : npix;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
+  for (long long p = p0; p < p1; ++p) {
+    const int px = (int)(p % W);
+    const int py = (int)((p / W) % H);
+    const float g = __bfloat162float(dy[p * dps + co]);
+    if (t == 4) ab += g;
+    const int iy = py + ky - 1, ix = px + kx - 1;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const __nv_bfloat16* xp = x + (p + (long long)(ky - 1) * W + (kx - 1)) * 3;
+    a0 += __bfloat162float(xp[0]) * g;
+    a1 += __bfloat162float(xp[1]) * g;
+    a2 += __bfloat162float(xp[2]) * g;
+  }
+  atomicAdd(&dw[(t * 3 + 0) * Cout + co], a0);
+  atomicAdd(&dw[(t * 3 + 1) * Cout + co], a1);
+  atomicAdd(&dw[(t * 3 + 2) * Cout + co], a2);
+  if (t == 4 && db) atomicAdd(&db[co], ab);
+}
+
+// ---- conv_out forward: x bf16 act [.,Cin], w f32 [9][Cin][3], y f32 [N,H,W,3] -----------
+__global__ void __launch_bounds__(128)
+cout3_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long xps, const float* __restrict__ w,
+                 const float* __restrict__ bias, int N, int H, int W, int Cin,
+                 float* __restrict__ y) {
+  extern __shared__ float sw[];   // [9][Cin][3]
+  for (int i = threadIdx.x; i < 27 * Cin; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long long npix = (long long)N * H * W;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(p % W);
+    const int py = (int)((p / W) % H);
+    float a0 = bias ? bias[0] : 0.f, a1 = bias ? bias[1] : 0.f, a2 = bias ? bias[2] : 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = py + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = px + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        const __nv_bfloat16* xp = x + (p + (long long)(ky - 1) * W + (kx - 1)) * xps;
+        const float* wp = sw + (ky * 3 + kx) * Cin * 3;
+        for (int c8 = 0; c8 < Cin; c8 += 8) {
+          const uint4 u = *reinterpret_cast<const uint4*>(xp + c8);
+          const float2 q0 = unpack_bf16x2(u.x), q1 = unpack_bf16x2(u.y), q2 = unpack_bf16x2(u.z),
+                       q3 = unpack_bf16x2(u.w);
+          const float v[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float* ww = wp + (c8 + j) * 3;
+            a0 += v[j] * ww[0]; a1 += v[j] * ww[1]; a2 += v[j] * ww[2];
+          }
+        }
+      }
+    }
+    y[p * 3 + 0] = a0; y[p * 3 + 1] = a1; y[p * 3 + 2] = a2;
+  }
+}
+
+// ---- conv_out dgrad: dx[p][ci] = sum_{t,co} dF[p - d(t)][co] * w[t][ci][co] ---------------
+__global__ void __launch_bounds__(256)
+cout3_dgrad_kernel(const float* __restrict__ dF, const float* __restrict__ w, int N, int H, int W,
+                   int Cin, __nv_bfloat16* __restrict__ dx, long long dxps) {
+  extern __shared__ float sw[];   // [9][Cin][3]
+  for (int i = threadIdx.x; i < 27 * Cin; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int vpp = Cin >> 3;
+  const long long total = (long long)N * H * W * vpp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vpp);
+    const long long p = i / vpp;
+    const int px = (int)(p % W);
+    const int py = (int)((p / W) % H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int oy = py - ky + 1;
+      if (oy < 0 || oy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ox = px - kx + 1;
+        if (ox < 0 || ox >= W) continue;
+        const float* g = dF + (p + (long long)(1 - ky) * W + (1 - kx)) * 3;
+        const float g0 = g[0], g1 = g[1], g2 = g[2];
+        const float* wp = sw + ((ky * 3 + kx) * Cin + cv * 8) * 3;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += g0 * wp[j * 3] + g1 * wp[j * 3 + 1] + g2 * wp[j * 3 + 2];
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(dx + p * dxps + cv * 8) = o;
+  }
+}
+
+// ---- conv_out wgrad: dW[t][ci][co] += sum_p x[p+d(t)][ci] * dF[p][co]; db[co] += sum dF ---
+__global__ void __launch_bounds__(576)
+cout3_wgrad_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
+                   const float* __restrict__ dF, int N, int H, int W, int Cin,
+                   float* __restrict__ dw, float* __restrict__ db) {
+  // blockDim = 9 * Cin (Cin == 64); thread = (tap, ci)
+  const int t = threadIdx.x / Cin, ci = threadIdx.x % Cin;
+  const int ky = t / 3, kx = t % 3;
+  const long long npix = (long long)N * H * W;
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per, p1 = (p0 + per < npix) ? p0 + per : npix;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  for (long long p = p0; p < p1; ++p) {
+    const int px = (int)(p % W);
+    const int py = (int)((p / W) % H);
+    const float g0 = dF[p * 3], g1 = dF[p * 3 + 1], g2 = dF[p * 3 + 2];
+    if (threadIdx.x == 0) { b0 += g0; b1 += g1; b2 += g2; }
+    const int iy = py + ky - 1, ix = px + kx - 1;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const float v = __bfloat162float(x[(p + (long long)(ky - 1) * W + (kx - 1)) * xps + ci]);
+    a0 += v * g0; a1 += v * g1; a2 += v * g2;
+  }
+  float* o = dw + ((long long)t * Cin + ci) * 3;
+  atomicAdd(o, a0); atomicAdd(o + 1, a1); atomicAdd(o + 2, a2);
+  if (threadIdx.x == 0 && db) { atomicAdd(db, b0); atomicAdd(db + 1, b1); atomicAdd(db + 2, b2); }
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdx_conv_in_fwd(const void* x_bf16, int N, int H, int W, const float* w_hwio,
+                    const float* bias, const fdx_act* y, void* stream) {
+  FDX_REQUIRE(x_bf16 && w_hwio && y && y->ptr, "conv_in_fwd: null pointer");
+  FDX_REQUIRE(y->n == N && y->h == H && y->w == W && y->c % 8 == 0 && y->c <= 256,
+              "conv_in_fwd: bad output shape");
+  const long long total = (long long)N * H * W * (y->c / 8);
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  cin3_fwd_kernel<<<(int)grid, 256, sizeof(float) * 28 * y->c, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x_bf16, w_hwio, bias, N, H, W, y->c, (__nv_bfloat16*)y->ptr,
+      y->pix_stride);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_conv_in_wgrad(const void* x_bf16, const fdx_act* dy, float* dw_hwio, float* dbias,
+                      void* stream) {
+  FDX_REQUIRE(x_bf16 && dy && dy->ptr && dw_hwio, "conv_in_wgrad: null pointer");
+  FDX_REQUIRE(dy->c == 64, "conv_in_wgrad: Cout must be 64 (got %d)", dy->c);
+  cin3_wgrad_kernel<<<148 * 2, 9 * 64, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x_bf16, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, dy->n, dy->h,
+      dy->w, dy->c, dw_hwio, dbias);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_conv_out_fwd(const fdx_act* x, const float* w_hwio, const float* bias, float* y_f32,
+                     void* stream) {
+  FDX_REQUIRE(x && x->ptr && w_hwio && y_f32, "conv_out_fwd: null pointer");
+  FDX_REQUIRE(x->c % 8 == 0 && x->c <= 256, "conv_out_fwd: bad Cin %d", x->c);
+  const long long npix = (long long)x->n * x->h * x->w;
+  long long grid = (npix + 127) / 128;
+  if (grid > 148 * 16) grid = 148 * 16;
+  cout3_fwd_kernel<<<(int)grid, 128, sizeof(float) * 27 * x->c, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, w_hwio, bias, x->n, x->h, x->w, x->c, y_f32);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_conv_out_dgrad(const float* dF, const float* w_hwio, const fdx_act* dx, void* stream) {
+  FDX_REQUIRE(dF && w_hwio && dx && dx->ptr, "conv_out_dgrad: null pointer");
+  FDX_REQUIRE(dx->c % 8 == 0 && dx->c <= 256, "conv_out_dgrad: bad Cin %d", dx->c);
+  const long long total = (long long)dx->n * dx->h * dx->w * (dx->c / 8);
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  cout3_dgrad_kernel<<<(int)grid, 256, sizeof(float) * 27 * dx->c, (cudaStream_t)stream>>>(
+      dF, w_hwio, dx->n, dx->h, dx->w, dx->c, (__nv_bfloat16*)dx->ptr, dx->pix_stride);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_conv_out_wgrad(const fdx_act* x, const float* dF, float* dw_hwio, float* dbias,
+                       void* stream) {
+  FDX_REQUIRE(x && x->ptr && dF && dw_hwio, "conv_out_wgrad: null pointer");
+  FDX_REQUIRE(x->c == 64, "conv_out_wgrad: Cin must be 64 (got %d)", x->c);
+  cout3_wgrad_kernel<<<148 * 2, 9 * 64, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, dF, x->n, x->h, x->w, x->c, dw_hwio, dbias);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+}  // extern "C"

@@ -384,7 +384,7 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
   FDX_REQUIRE(L.mode >= TC_KK && L.mode <= TC_MNMN, "tc: bad mode %d", L.mode);
   FDX_REQUIRE(L.ntaps >= 1 && L.ntaps <= 9, "tc: bad ntaps %d", L.ntaps);
   FDX_REQUIRE(L.es == 1 || L.es == 2, "tc: bad element stride %d", L.es);
-  FDX_REQUIRE(L.Ncols > 0 && L.Ncols % 64 == 0, "tc: Ncols=%d must be a multiple of 64", L.Ncols);
+  FDX_REQUIRE(L.Ncols > 0 && L.Ncols % 32 == 0, "tc: Ncols=%d must be a multiple of 32", L.Ncols);
   FDX_REQUIRE(L.A.strides[0] == 1 && L.B.strides[0] == 1, "tc: innermost strides must be 1");
 
   TcDev d{};
@@ -423,8 +423,8 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
   const long long pix_blocks = (long long)d.nxb * d.nyb * d.nnb;
 
   if (L.mode != TC_MNMN) {
-    while (BN > 64 && pix_blocks * (L.Ncols / BN) < 2LL * fdx_num_sms()) BN /= 2;
-    d.nblks = L.Ncols / BN;
+    while (BN > 64 && pix_blocks * ((L.Ncols + BN - 1) / BN) < 2LL * fdx_num_sms()) BN /= 2;
+    d.nblks = (L.Ncols + BN - 1) / BN;
     d.kchunks = (L.K + kBK - 1) / kBK;
     d.ntiles = (int)(pix_blocks * d.nblks);
     d.splits = 1;
@@ -432,7 +432,7 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
     FDX_REQUIRE(!L.res || !L.out_atomic, "tc: residual with atomic output unsupported");
   } else {
     if (BN > 128) BN = 128;   // 2 A blocks + BN/64 B blocks of 8 KB per stage
-    d.nblks = L.Ncols / BN;
+    d.nblks = (L.Ncols + BN - 1) / BN;
     d.mblks = (L.M + 127) / 128;
     d.kchunks = 0;
     long long base_tiles = (long long)L.ntaps * d.mblks * d.nblks;

@@ -1,0 +1,600 @@
+"""`Unet` - the reference's UNet denoiser (flaxdiff/models/simple_unet.py:11-222) rebuilt as
+an explicit forward / backward program over libfdx kernels.
+
+API kept from the reference (flax.linen module surface):
+    model = Unet(output_channels=3, emb_features=256, feature_depths=(64,128,256,512),
+                 attention_configs=(None, None, None, {"heads": 8}), num_res_blocks=2,
+                 num_middle_res_blocks=1, norm_groups=8, dtype=torch.bfloat16)
+    params = model.init(key, x=ones(1,H,W,3), temb=ones(1), textcontext=None)   # {'params': tree}
+    y = model.apply(params, x, temb, textcontext)                                  # (B,H,W,3)
+Parameter names / layouts are flax's (HWIO conv kernels, (in,out) dense kernels, names as in
+pretrained/*/_METADATA): `ConvLayer_0/conv/kernel`, `down_0_residual_0/norm1/scale`, ...
+
+Execution design (B200-first, not a translation of the flax module tree):
+  * activations are NHWC bf16; every skip concatenation (simple_unet.py:145,196) is a
+    channel *slot* of a pre-allocated buffer, so producers write it in place and the
+    concat is free; TMA reads the strided views directly;
+  * each ResidualBlock (models/common.py:284-338) is: GN stats -> GN apply+SiLU ->
+    conv3x3 [tcgen05] with bias + timestep row-vector fused in the epilogue -> GN stats ->
+    apply+SiLU -> conv3x3 with bias + residual fused; the 1x1 residual conv is a GEMM;
+  * backward is an explicit tape (no autograd engine): dgrad / wgrad on the same tcgen05
+    engine, GroupNorm backward in two streaming passes, gradients accumulated at forks by
+    the consumer kernels' accumulate flags;
+  * reference quirks kept: res-blocks of a down level keep the incoming width, Upsample
+    widths feature_depths[-i] (i=0 -> [0]), attention residual added to the normalised
+    tensor; `textcontext=None` selects self-attention (A.4).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from .. import ops, utils
+from .._lib import GEMM_KK, GEMM_KMN, GEMM_MNMN, FdxError
+from .params import FlatParams, ParamLayout, from_tree
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+RES_EPS = 1e-4      # ResidualBlock.norm_epsilon, models/common.py:271
+OUT_EPS = 1e-6      # flax GroupNorm default epsilon for Unet.conv_out_norm (simple_unet.py:26)
+ATTN_EPS = 1e-4     # TransformerBlock.norm_epsilon, models/attention.py:319
+
+
+class Node:
+    """An activation view plus (lazily) its gradient view."""
+    __slots__ = ("t", "g", "gw", "parent")
+
+    def __init__(self, t: torch.Tensor, parent: Optional["Node"] = None):
+        self.t = t
+        self.g: Optional[torch.Tensor] = None
+        self.gw = False          # gradient buffer holds valid data
+        self.parent = parent
+
+    def grad_buf(self) -> torch.Tensor:
+        if self.g is None:
+            self.g = torch.empty(tuple(self.t.shape), dtype=BF16, device=self.t.device)
+        return self.g
+
+
+class Unet:
+    def __init__(self, output_channels: int = 3, emb_features: int = 64 * 4,
+                 feature_depths: Sequence[int] = (64, 128, 256, 512),
+                 attention_configs: Sequence[Optional[dict]] = ({"heads": 8},) * 4,
+                 num_res_blocks: int = 2, num_middle_res_blocks: int = 1, activation="swish",
+                 norm_groups: int = 8, dtype=None, precision=None, named_norms: bool = False):
+        self.output_channels = output_channels
+        self.emb_features = emb_features
+        self.feature_depths = tuple(feature_depths)
+        self.attention_configs = tuple(attention_configs)
+        self.num_res_blocks = num_res_blocks
+        self.num_middle_res_blocks = num_middle_res_blocks
+        self.activation = activation
+        self.norm_groups = norm_groups
+        self.dtype = dtype
+        self.precision = precision
+        self.named_norms = named_norms
+        if norm_groups <= 0:
+            raise FdxError("Unet: norm_groups=0 (RMSNorm blocks) is not on the supported hot path")
+        if output_channels != 3:
+            raise FdxError("Unet: output_channels must be 3 (pixel-space configs of BASELINE.json)")
+        if len(self.attention_configs) != len(self.feature_depths):
+            raise FdxError("Unet: attention_configs must have one entry per level")
+        for c in self.attention_configs:
+            if c is not None and not c.get("only_pure_attention", True):
+                raise FdxError("Unet: only_pure_attention=False is not implemented yet")
+            if c is not None and c.get("use_projection", False):
+                raise FdxError("Unet: use_projection=True is not implemented yet")
+        self._n1 = "GroupNorm_0" if named_norms else "norm1"
+        self._n2 = "GroupNorm_1" if named_norms else "norm2"
+        self._nout = "GroupNorm_0" if named_norms else "conv_out_norm"
+        self._layout: Optional[ParamLayout] = None
+        self._freqs: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ structure
+    def _plan(self):
+        """Static structure: list of blocks with channel counts (simple_unet.py:33-222)."""
+        fd = self.feature_depths
+        L = len(fd)
+        blocks = []
+        c = fd[0]
+        blocks.append(("conv_in", "ConvLayer_0", 3, c))
+        skips = [c]
+        for i, (dim_out, acfg) in enumerate(zip(fd, self.attention_configs)):
+            dim_in = c
+            for j in range(self.num_res_blocks):
+                blocks.append(("res", f"down_{i}_residual_{j}", c, dim_in))
+                c = dim_in
+                if acfg is not None and j == self.num_res_blocks - 1:
+                    blocks.append(("attn", f"down_{i}_attention_{j}", c, acfg))
+                blocks.append(("push", None, c, None))
+                skips.append(c)
+            if i != L - 1:
+                blocks.append(("down", f"down_{i}_downsample", c, dim_out))
+                c = dim_out
+        mid = fd[-1]
+        macfg = self.attention_configs[-1]
+        for j in range(self.num_middle_res_blocks):
+            blocks.append(("res", f"middle_res1_{j}", c, mid))
+            c = mid
+            if macfg is not None and j == self.num_middle_res_blocks - 1:
+                blocks.append(("attn", f"middle_attention_{j}", c, macfg))
+            blocks.append(("res", f"middle_res2_{j}", c, mid))
+        for i, (dim_out, acfg) in enumerate(zip(reversed(fd), reversed(self.attention_configs))):
+            for j in range(self.num_res_blocks):
+                cs = skips.pop()
+                blocks.append(("cat", None, c, cs))
+                blocks.append(("res", f"up_{i}_residual_{j}", c + cs, dim_out))
+                c = dim_out
+                if acfg is not None and j == self.num_res_blocks - 1:
+                    blocks.append(("attn", f"up_{i}_attention_{j}", c, acfg))
+            if i != L - 1:
+                up_c = fd[-i] if i > 0 else fd[0]   # feature_depths[-i]; -0 == 0 (quirk, A.1)
+                blocks.append(("up", f"up_{i}_upsample", c, up_c))
+                c = up_c
+        blocks.append(("conv", "ConvLayer_1", c, fd[0]))
+        c = fd[0]
+        cs = skips.pop()
+        blocks.append(("cat", None, c, cs))
+        blocks.append(("res", "final_residual", c + cs, fd[0]))
+        c = fd[0]
+        blocks.append(("out", "ConvLayer_2", c, self.output_channels))
+        assert not skips
+        return blocks
+
+    def param_specs(self):
+        E = self.emb_features
+        specs = [("TimeProjection_0/DenseGeneral_0/kernel", (E, E)), ("TimeProjection_0/DenseGeneral_0/bias", (E,)),
+                 ("TimeProjection_0/DenseGeneral_1/kernel", (E, E)), ("TimeProjection_0/DenseGeneral_1/bias", (E,))]
+        for kind, name, cin, cout in self._plan():
+            if kind in ("conv_in", "conv", "out"):
+                specs += [(f"{name}/conv/kernel", (3, 3, cin, cout)), (f"{name}/conv/bias", (cout,))]
+            elif kind == "res":
+                specs += [(f"{name}/{self._n1}/scale", (cin,)), (f"{name}/{self._n1}/bias", (cin,)),
+                          (f"{name}/conv1/conv/kernel", (3, 3, cin, cout)), (f"{name}/conv1/conv/bias", (cout,)),
+                          (f"{name}/temb_projection/kernel", (E, cout)), (f"{name}/temb_projection/bias", (cout,)),
+                          (f"{name}/{self._n2}/scale", (cout,)), (f"{name}/{self._n2}/bias", (cout,)),
+                          (f"{name}/conv2/conv/kernel", (3, 3, cout, cout)), (f"{name}/conv2/conv/bias", (cout,))]
+                if cin != cout:
+                    specs += [(f"{name}/residual_conv/conv/kernel", (1, 1, cin, cout)),
+                              (f"{name}/residual_conv/conv/bias", (cout,))]
+            elif kind in ("down", "up"):
+                specs += [(f"{name}/ConvLayer_0/conv/kernel", (3, 3, cin, cout)),
+                          (f"{name}/ConvLayer_0/conv/bias", (cout,))]
+            elif kind == "attn":
+                h = cout["heads"]
+                d = cin // h
+                base = f"{name}/Attention/Attention2"
+                specs += [(f"{name}/RMSNorm_0/scale", (cin,)),
+                          (f"{base}/to_q/kernel", (cin, h, d)), (f"{base}/to_k/kernel", (cin, h, d)),
+                          (f"{base}/to_v/kernel", (cin, h, d)), (f"{base}/to_out_0/kernel", (h, d, cin))]
+        specs += [(f"{self._nout}/scale", (self.feature_depths[0],)), (f"{self._nout}/bias", (self.feature_depths[0],))]
+        return specs
+
+    def layout(self) -> ParamLayout:
+        if self._layout is None:
+            self._layout = ParamLayout(self.param_specs())
+        return self._layout
+
+    # ------------------------------------------------------------------ init
+    def init(self, key, x=None, temb=None, textcontext=None, device=None) -> FlatParams:
+        """flax `model.init(key, **ones)` (trainer/diffusion_trainer.py:107-108): lecun-normal
+        kernels (flax default kernel_init), zero biases, unit norm scales."""
+        if device is None:
+            device = x.device if isinstance(x, torch.Tensor) else torch.device("cuda")
+        lay = self.layout()
+        flat = torch.zeros(lay.total, dtype=F32, device=device)
+        fp = FlatParams(lay, flat)
+        if isinstance(key, int):
+            key = utils.PRNGKey(key)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(utils.key_to_seed(tuple(key)))
+        for name, t in fp.named.items():
+            leaf = name.rsplit('/', 1)[1]
+            if leaf == "scale":
+                t.fill_(1.0)
+            elif leaf == "kernel":
+                if t.dim() == 4:
+                    fan_in = t.shape[0] * t.shape[1] * t.shape[2]
+                elif t.dim() == 3 and name.endswith("to_out_0/kernel"):
+                    fan_in = t.shape[0] * t.shape[1]
+                else:
+                    fan_in = t.shape[0]
+                std = math.sqrt(1.0 / fan_in) / 0.87962566103423978
+                torch.nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=gen)
+        return fp
+
+    def _fourier_freqs(self, device) -> torch.Tensor:
+        """FourierEmbedding.freqs = jax.random.normal(PRNGKey(42), (features//2,)) * 16
+        (models/common.py:101-102): a constant, not a parameter."""
+        k = str(device)
+        if k not in self._freqs:
+            f = utils.normal(utils.PRNGKey(42), self.emb_features // 2) * 16.0
+            self._freqs[k] = torch.from_numpy(f.astype("float32")).to(device)
+        return self._freqs[k]
+
+    # ------------------------------------------------------------------ public apply
+    def _as_flat(self, params, device) -> FlatParams:
+        if isinstance(params, FlatParams):
+            return params
+        return from_tree(self.layout(), params, device)
+
+    def apply(self, params, x: torch.Tensor, temb: torch.Tensor, textcontext=None) -> torch.Tensor:
+        """`model.apply(params, x, temb, textcontext)` (general_diffusion_trainer.py:292)."""
+        if not x.is_cuda:
+            raise FdxError("Unet.apply: CUDA tensors required (no CPU path in flaxdiff_b200)")
+        fp = self._as_flat(params, x.device)
+        xin = x if x.dtype == BF16 else x.to(BF16)
+        out, _ = self.forward(fp, xin.contiguous(), temb, textcontext, save=False)
+        return out
+
+    # ------------------------------------------------------------------ forward program
+    def forward(self, fp: FlatParams, x_bf16: torch.Tensor, temb: torch.Tensor, textcontext=None,
+                save: bool = True):
+        """Returns (F f32 [B,H,W,3], tape or None)."""
+        if textcontext is not None and any(c is not None for c in self.attention_configs):
+            raise FdxError("Unet: cross-attention to textcontext is not implemented yet; pass "
+                           "textcontext=None for self-attention")
+        W = fp.named
+        W16 = fp.shadow()
+        B, H, Wd, _ = x_bf16.shape
+        dev = x_bf16.device
+        G = self.norm_groups
+        plan = self._plan()
+        tape: List[tuple] = []
+
+        # timestep embedding (f32 MLP) -----------------------------------------
+        tp = "TimeProjection_0/DenseGeneral_"
+        temb = temb.reshape(-1).to(F32)
+        if temb.numel() == 1 and B > 1:
+            temb = temb.expand(B)
+        emb, emb16, temb_saved = ops.time_embed_fwd(
+            temb, self._fourier_freqs(dev), W[tp + "0/kernel"], W[tp + "0/bias"], W[tp + "1/kernel"],
+            W[tp + "1/bias"])
+
+        # concat slot buffers: walk the plan once to find (x channels, skip channels, resolution)
+        # skip k is produced by the k-th ("conv_in" | "push"); consumed by "cat" in LIFO order.
+        res_of_skip, ch_of_skip = [], []
+        h, w = H, Wd
+        for kind, name, cin, cout in plan:
+            if kind == "conv_in":
+                res_of_skip.append((h, w)); ch_of_skip.append(cout)
+            elif kind == "push":
+                res_of_skip.append((h, w)); ch_of_skip.append(cin)
+            elif kind == "down":
+                h, w = h // 2, w // 2
+            elif kind == "up":
+                h, w = h * 2, w * 2
+        cat_cx = {}
+        stack = list(range(len(ch_of_skip)))
+        for kind, name, cin, cout in plan:
+            if kind == "cat":
+                k = stack.pop()
+                cat_cx[k] = cin
+        cat_nodes = {}
+        for k, cx in cat_cx.items():
+            hh, ww = res_of_skip[k]
+            buf = torch.empty((B, hh, ww, cx + ch_of_skip[k]), dtype=BF16, device=dev)
+            parent = Node(buf)
+            cat_nodes[k] = (parent, Node(buf[..., :cx], parent), Node(buf[..., cx:], parent))
+
+        def new_node(hh, ww, c):
+            return Node(torch.empty((B, hh, ww, c), dtype=BF16, device=dev))
+
+        # which op output must land in which slot: an op's output goes to the x-part of the cat
+        # that follows it, or to the skip slot if a "push"/"conv_in" applies to it.
+        skip_idx = 0
+        pop_stack: List[int] = []
+        h, w = H, Wd
+        cur: Optional[Node] = None
+        n_blocks = len(plan)
+
+        def out_node(idx, hh, ww, c) -> Node:
+            """Destination of the op at plan[idx]."""
+            nxt = plan[idx + 1][0] if idx + 1 < n_blocks else None
+            if nxt == "cat":
+                k = pop_stack[-1]
+                return cat_nodes[k][1]
+            if nxt == "push":
+                return cat_nodes[skip_idx][2]
+            return new_node(hh, ww, c)
+
+        for idx, (kind, name, cin, cout) in enumerate(plan):
+            if kind == "conv_in":
+                dst = cat_nodes[0][2]
+                ops.conv_in_fwd(x_bf16, W[name + "/conv/kernel"], W[name + "/conv/bias"], dst.t)
+                tape.append(("conv_in", name, x_bf16, dst))
+                pop_stack.append(0)
+                skip_idx = 1
+                cur = dst
+            elif kind == "push":
+                pop_stack.append(skip_idx)
+                skip_idx += 1
+            elif kind == "cat":
+                k = pop_stack.pop()
+                cur = cat_nodes[k][0]
+            elif kind == "res":
+                dst = out_node(idx, h, w, cout)
+                rec = self._res_fwd(name, cur, dst, emb16, W, W16, G, RES_EPS)
+                tape.append(rec)
+                cur = dst
+            elif kind == "attn":
+                dst = out_node(idx, h, w, cin)
+                rec = self._attn_fwd(name, cur, dst, cout["heads"], W, W16)
+                tape.append(rec)
+                cur = dst
+            elif kind == "down":
+                h, w = h // 2, w // 2
+                dst = out_node(idx, h, w, cout)
+                ops.conv3x3_fwd(cur.t, W16[name + "/ConvLayer_0/conv/kernel"],
+                                W[name + "/ConvLayer_0/conv/bias"], out=dst.t, stride=2)
+                tape.append(("down", name, cur, dst))
+                cur = dst
+            elif kind == "up":
+                u = ops.upsample2x(cur.t)
+                h, w = h * 2, w * 2
+                dst = out_node(idx, h, w, cout)
+                ops.conv3x3_fwd(u, W16[name + "/ConvLayer_0/conv/kernel"],
+                                W[name + "/ConvLayer_0/conv/bias"], out=dst.t)
+                tape.append(("up", name, cur, dst, u if save else None))
+                cur = dst
+            elif kind == "conv":
+                dst = out_node(idx, h, w, cout)
+                ops.conv3x3_fwd(cur.t, W16[name + "/conv/kernel"], W[name + "/conv/bias"], out=dst.t)
+                tape.append(("conv", name, cur, dst))
+                cur = dst
+            elif kind == "out":
+                st = ops.groupnorm_stats(cur.t, G)
+                a = ops.groupnorm_apply(cur.t, G, st, W[self._nout + "/scale"], W[self._nout + "/bias"],
+                                        OUT_EPS, True)
+                Fo = ops.conv_out_fwd(a, W[name + "/conv/kernel"], W[name + "/conv/bias"])
+                tape.append(("out", name, cur, st, a))
+                cur = None
+        if not save:
+            return Fo, None
+        return Fo, {"tape": tape, "emb16": emb16, "temb_saved": temb_saved, "B": B}
+
+    # ------------------------------------------------------------------ blocks: forward
+    def _res_fwd(self, name, xin: Node, dst: Node, emb16, W, W16, G, eps):
+        x = xin.t
+        cin, cout = x.shape[-1], dst.t.shape[-1]
+        st1 = ops.groupnorm_stats(x, G)
+        a1 = ops.groupnorm_apply(x, G, st1, W[f"{name}/{self._n1}/scale"], W[f"{name}/{self._n1}/bias"], eps, True)
+        row = ops.linear_fwd(emb16, W16[f"{name}/temb_projection/kernel"],
+                             bias=W[f"{name}/temb_projection/bias"], out_dtype=F32)
+        hmid = ops.conv3x3_fwd(a1, W16[f"{name}/conv1/conv/kernel"], W[f"{name}/conv1/conv/bias"], rowvec=row)
+        st2 = ops.groupnorm_stats(hmid, G)
+        a2 = ops.groupnorm_apply(hmid, G, st2, W[f"{name}/{self._n2}/scale"], W[f"{name}/{self._n2}/bias"], eps, True)
+        if cin != cout:
+            Bn, hh, ww, _ = x.shape
+            r = torch.empty((Bn, hh, ww, cout), dtype=BF16, device=x.device)
+            ops.gemm(GEMM_KMN, x, W16[f"{name}/residual_conv/conv/kernel"], r, Bn * hh * ww, cout, cin,
+                     x.stride(2), cout, cout, bias=W[f"{name}/residual_conv/conv/bias"])
+        else:
+            r = x
+        ops.conv3x3_fwd(a2, W16[f"{name}/conv2/conv/kernel"], W[f"{name}/conv2/conv/bias"], res=r, out=dst.t)
+        return ("res", name, xin, dst, st1, a1, hmid, st2, a2)
+
+    def _attn_fwd(self, name, xin: Node, dst: Node, heads, W, W16):
+        """TransformerBlock(only_pure_attention) (models/attention.py:321-380): xn = RMSNorm(x);
+        out = xn + to_out(softmax(q k^T / sqrt(d)) v), context = xn (self-attention)."""
+        x = xin.t
+        Bn, hh, ww, C = x.shape
+        L = hh * ww
+        d = C // heads
+        base = f"{name}/Attention/Attention2"
+        xn = ops.rmsnorm_fwd(x, W[f"{name}/RMSNorm_0/scale"], ATTN_EPS)
+        x2 = xn.view(Bn * L, C)
+        q = ops.linear_fwd(x2, W16[f"{base}/to_q/kernel"].view(C, C))
+        k = ops.linear_fwd(x2, W16[f"{base}/to_k/kernel"].view(C, C))
+        v = ops.linear_fwd(x2, W16[f"{base}/to_v/kernel"].view(C, C))
+        S = torch.empty((Bn, heads, L, L), dtype=F32, device=x.device)
+        ops.gemm(GEMM_KK, q, k, S, L, L, d, C, C, L, batch1=heads, batch2=Bn,
+                 a_s=(d, L * C), b_s=(d, L * C), d_s=(L * L, heads * L * L), alpha=d ** -0.5)
+        P = ops.softmax_fwd(S)
+        del S
+        o = torch.empty((Bn * L, C), dtype=BF16, device=x.device)
+        ops.gemm(GEMM_KMN, P, v, o, L, d, L, L, C, C, batch1=heads, batch2=Bn,
+                 a_s=(L * L, heads * L * L), b_s=(d, L * C), d_s=(d, L * C))
+        out2 = dst.t
+        ops.gemm(GEMM_KMN, o, W16[f"{base}/to_out_0/kernel"].view(C, C), out2, Bn * L, C, C, C, C,
+                 out2.stride(2), res=xn, r_ld=C)
+        return ("attn", name, xin, dst, heads, xn, q, k, v, P, o)
+
+    # ------------------------------------------------------------------ backward program
+    def backward(self, fp: FlatParams, saved: dict, dF: torch.Tensor, grads: FlatParams):
+        """Accumulates d(loss)/d(params) into `grads` (f32, caller zeroes it) given dF = dL/dF."""
+        W, W16, Gd = fp.named, fp.shadow(), grads.named
+        G = self.norm_groups
+        emb16 = saved["emb16"]
+        B = saved["B"]
+        dev = dF.device
+        demb = torch.zeros((B, self.emb_features), dtype=F32, device=dev)
+
+        def want(node: Node):
+            """(grad buffer, accumulate?) for a consumer adding into node's gradient."""
+            if node.g is None:
+                if node.parent is not None:
+                    par = node.parent
+                    if par.g is None:
+                        par.g = torch.empty(tuple(par.t.shape), dtype=BF16, device=dev)
+                    off = node.t.storage_offset() - par.t.storage_offset()
+                    node.g = par.g[..., off:off + node.t.shape[-1]]
+                else:
+                    node.grad_buf()
+            acc = node.gw
+            node.gw = True
+            return node.g, acc
+
+        def grad_of(node: Node) -> torch.Tensor:
+            if node.g is None or not node.gw:
+                raise FdxError("backward: gradient of an activation was never produced")
+            return node.g
+
+        def mark_children_written(parent: Node, children):
+            for ch in children:
+                if ch.g is None:
+                    off = ch.t.storage_offset() - parent.t.storage_offset()
+                    ch.g = parent.g[..., off:off + ch.t.shape[-1]]
+                ch.gw = True
+
+        # parents -> children map for concat buffers
+        children: Dict[int, List[Node]] = {}
+        for rec in saved["tape"]:
+            for obj in rec:
+                if isinstance(obj, Node) and obj.parent is not None:
+                    lst = children.setdefault(id(obj.parent), [])
+                    if all(o is not obj for o in lst):
+                        lst.append(obj)
+
+        for rec in reversed(saved["tape"]):
+            kind, name = rec[0], rec[1]
+            if kind == "out":
+                _, _, xin, st, a = rec
+                da = torch.empty_like(a)
+                ops.conv_out_dgrad(dF, W[name + "/conv/kernel"], da)
+                ops.conv_out_wgrad(a, dF, Gd[name + "/conv/kernel"], Gd[name + "/conv/bias"])
+                dx, acc = want(xin)
+                ops.groupnorm_bwd(xin.t, da, G, st, W[self._nout + "/scale"], W[self._nout + "/bias"], OUT_EPS,
+                                  True, Gd[self._nout + "/scale"], Gd[self._nout + "/bias"], dx, acc)
+            elif kind == "res":
+                self._res_bwd(rec, W, W16, Gd, G, emb16, demb, want, grad_of)
+                xin = rec[2]
+                if id(xin) in children:
+                    mark_children_written(xin, children[id(xin)])
+            elif kind == "attn":
+                self._attn_bwd(rec, W, W16, Gd, want, grad_of)
+            elif kind == "conv":
+                _, _, xin, dst = rec
+                dy = grad_of(dst)
+                ops.conv3x3_wgrad(xin.t, dy, Gd[name + "/conv/kernel"])
+                ops.colsum(dy, False, out=Gd[name + "/conv/bias"])
+                dx, acc = want(xin)
+                ops.conv3x3_dgrad(dy, W16[name + "/conv/kernel"], dx, accumulate=acc)
+            elif kind == "down":
+                _, _, xin, dst = rec
+                dy = grad_of(dst)
+                kn = name + "/ConvLayer_0/conv/"
+                ops.conv3x3_wgrad(xin.t, dy, Gd[kn + "kernel"], stride=2)
+                ops.colsum(dy, False, out=Gd[kn + "bias"])
+                dx, acc = want(xin)
+                ops.conv3x3_dgrad(dy, W16[kn + "kernel"], dx, stride=2, accumulate=acc)
+            elif kind == "up":
+                _, _, xin, dst, u = rec
+                dy = grad_of(dst)
+                kn = name + "/ConvLayer_0/conv/"
+                if u is None:
+                    u = ops.upsample2x(xin.t)
+                ops.conv3x3_wgrad(u, dy, Gd[kn + "kernel"])
+                ops.colsum(dy, False, out=Gd[kn + "bias"])
+                du = torch.empty_like(u)
+                ops.conv3x3_dgrad(dy, W16[kn + "kernel"], du)
+                dx, acc = want(xin)
+                ops.upsample2x_bwd(du, dx, accumulate=acc)
+            elif kind == "conv_in":
+                _, _, x_bf16, dst = rec
+                dy = grad_of(dst)
+                ops.conv_in_wgrad(x_bf16, dy, Gd[name + "/conv/kernel"], Gd[name + "/conv/bias"])
+        # timestep-embedding MLP
+        tp = "TimeProjection_0/DenseGeneral_"
+        ops.time_embed_bwd(demb, saved["temb_saved"], W[tp + "1/kernel"], Gd[tp + "0/kernel"], Gd[tp + "0/bias"],
+                           Gd[tp + "1/kernel"], Gd[tp + "1/bias"])
+
+    def _res_bwd(self, rec, W, W16, Gd, G, emb16, demb, want, grad_of):
+        _, name, xin, dst, st1, a1, hmid, st2, a2 = rec
+        x = xin.t
+        cin, cout = x.shape[-1], dst.t.shape[-1]
+        dout = grad_of(dst)
+        Bn, hh, ww, _ = x.shape
+        E = emb16.shape[1]
+        # conv2
+        ops.conv3x3_wgrad(a2, dout, Gd[f"{name}/conv2/conv/kernel"])
+        ops.colsum(dout, False, out=Gd[f"{name}/conv2/conv/bias"])
+        da2 = torch.empty_like(a2)
+        ops.conv3x3_dgrad(dout, W16[f"{name}/conv2/conv/kernel"], da2)
+        # norm2 + silu
+        dh = torch.empty_like(hmid)
+        ops.groupnorm_bwd(hmid, da2, G, st2, W[f"{name}/{self._n2}/scale"], W[f"{name}/{self._n2}/bias"], RES_EPS,
+                          True, Gd[f"{name}/{self._n2}/scale"], Gd[f"{name}/{self._n2}/bias"], dh, False)
+        del da2
+        # timestep row-vector and conv1 bias
+        drow = ops.colsum(dh, True)                                   # [B, cout] f32
+        ops.colsum(dh, False, out=Gd[f"{name}/conv1/conv/bias"])
+        Gd[f"{name}/temb_projection/bias"].copy_(Gd[f"{name}/conv1/conv/bias"])
+        drow16 = ops.cast_f32_bf16(drow)
+        ops.gemm(GEMM_MNMN, emb16, drow16, Gd[f"{name}/temb_projection/kernel"], E, cout, Bn, E, cout, cout,
+                 atomic=True, reduce_batch=True)
+        ops.gemm(GEMM_KK, drow16, W16[f"{name}/temb_projection/kernel"], demb, Bn, E, cout, cout, cout, E,
+                 atomic=True)
+        # conv1
+        ops.conv3x3_wgrad(a1, dh, Gd[f"{name}/conv1/conv/kernel"])
+        da1 = torch.empty_like(a1)
+        ops.conv3x3_dgrad(dh, W16[f"{name}/conv1/conv/kernel"], da1)
+        del dh
+        # norm1 + silu -> dx
+        dx, acc = want(xin)
+        ops.groupnorm_bwd(x, da1, G, st1, W[f"{name}/{self._n1}/scale"], W[f"{name}/{self._n1}/bias"], RES_EPS, True,
+                          Gd[f"{name}/{self._n1}/scale"], Gd[f"{name}/{self._n1}/bias"], dx, acc)
+        # residual path
+        if cin != cout:
+            kn = f"{name}/residual_conv/conv/"
+            M = Bn * hh * ww
+            ops.gemm(GEMM_MNMN, x, dout, Gd[kn + "kernel"], cin, cout, M, x.stride(2), dout.stride(2), cout,
+                     atomic=True, reduce_batch=True)
+            Gd[kn + "bias"].copy_(Gd[f"{name}/conv2/conv/bias"])
+            ops.gemm(GEMM_KK, dout, W16[kn + "kernel"].view(cin, cout), dx, M, cin, cout, dout.stride(2), cout,
+                     dx.stride(2), res=dx, r_ld=dx.stride(2))
+        else:
+            ops.act_add(dx, dout, dx)
+
+    def _attn_bwd(self, rec, W, W16, Gd, want, grad_of):
+        _, name, xin, dst, heads, xn, q, k, v, P, o = rec
+        x = xin.t
+        Bn, hh, ww, C = x.shape
+        L = hh * ww
+        d = C // heads
+        base = f"{name}/Attention/Attention2"
+        dout = grad_of(dst)                      # [B,h,w,C] view
+        M = Bn * L
+        dev = x.device
+        alpha = d ** -0.5
+        # out = xn + o @ Wo
+        Wo16 = W16[f"{base}/to_out_0/kernel"].view(C, C)
+        ops.gemm(GEMM_MNMN, o, dout, Gd[f"{base}/to_out_0/kernel"], C, C, M, C, dout.stride(2), C,
+                 atomic=True, reduce_batch=True)
+        do = torch.empty((M, C), dtype=BF16, device=dev)
+        ops.gemm(GEMM_KK, dout, Wo16, do, M, C, C, dout.stride(2), C, C)
+        # o = P v
+        dv = torch.empty((M, C), dtype=BF16, device=dev)
+        ops.gemm(GEMM_MNMN, P, do, dv, L, d, L, L, C, C, batch1=heads, batch2=Bn,
+                 a_s=(L * L, heads * L * L), b_s=(d, L * C), d_s=(d, L * C))
+        dP = torch.empty((Bn, heads, L, L), dtype=F32, device=dev)
+        ops.gemm(GEMM_KK, do, v, dP, L, L, d, C, C, L, batch1=heads, batch2=Bn,
+                 a_s=(d, L * C), b_s=(d, L * C), d_s=(L * L, heads * L * L))
+        dS = ops.softmax_bwd(P, dP, alpha)
+        del dP
+        dq = torch.empty((M, C), dtype=BF16, device=dev)
+        ops.gemm(GEMM_KMN, dS, k, dq, L, d, L, L, C, C, batch1=heads, batch2=Bn,
+                 a_s=(L * L, heads * L * L), b_s=(d, L * C), d_s=(d, L * C))
+        dk = torch.empty((M, C), dtype=BF16, device=dev)
+        ops.gemm(GEMM_MNMN, dS, q, dk, L, d, L, L, C, C, batch1=heads, batch2=Bn,
+                 a_s=(L * L, heads * L * L), b_s=(d, L * C), d_s=(d, L * C))
+        del dS
+        # projections: y = xn @ Wx
+        x2 = xn.view(M, C)
+        dxn = torch.empty((Bn, hh, ww, C), dtype=BF16, device=dev)
+        dxn2 = dxn.view(M, C)
+        first = True
+        for nm, dy in (("to_q", dq), ("to_k", dk), ("to_v", dv)):
+            ops.gemm(GEMM_MNMN, x2, dy, Gd[f"{base}/{nm}/kernel"], C, C, M, C, C, C, atomic=True,
+                     reduce_batch=True)
+            Wx = W16[f"{base}/{nm}/kernel"].view(C, C)
+            if first:
+                # dxn = dout (residual) + dy Wx^T
+                ops.gemm(GEMM_KK, dy, Wx, dxn2, M, C, C, C, C, C, res=dout, r_ld=dout.stride(2))
+                first = False
+            else:
+                ops.gemm(GEMM_KK, dy, Wx, dxn2, M, C, C, C, C, C, res=dxn2, r_ld=C)
+        dx, acc = want(xin)
+        ops.rmsnorm_bwd(x, dxn, W[f"{name}/RMSNorm_0/scale"], ATTN_EPS, dx, Gd[f"{name}/RMSNorm_0/scale"], acc)

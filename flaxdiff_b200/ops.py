@@ -90,3 +90,252 @@ def linear_fwd(x2d: torch.Tensor, w_kn: torch.Tensor, out: Optional[torch.Tensor
         out = torch.empty((M, N), dtype=out_dtype, device=x2d.device)
     return gemm(GEMM_KMN, x2d, w_kn, out, M, N, K, x2d.stride(0), N, out.stride(0), bias=bias,
                 res=res, r_ld=(res.stride(0) if res is not None else 0))
+
+
+# --------------------------------------------------------------------------- norms
+def groupnorm_stats(x: torch.Tensor, groups: int) -> torch.Tensor:
+    stats = torch.empty((x.shape[0], groups, 2), dtype=torch.float32, device=x.device)
+    check(load().fdx_groupnorm_stats(ctypes.byref(act(x, "x")), ctypes.c_int(groups), ptr(stats),
+                                     stream_ptr()), "groupnorm_stats")
+    return stats
+
+
+def groupnorm_apply(x, groups, stats, gamma, beta, eps: float, silu: bool, out=None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    check(load().fdx_groupnorm_apply(ctypes.byref(act(x, "x")), ctypes.c_int(groups), ptr(stats),
+                                     ptr(gamma), ptr(beta), ctypes.c_float(eps),
+                                     ctypes.c_int(1 if silu else 0), ctypes.byref(act(out, "out")),
+                                     stream_ptr()), "groupnorm_apply")
+    return out
+
+
+def groupnorm_bwd(x, dy, groups, stats, gamma, beta, eps, silu, dgamma, dbeta, dx,
+                  accumulate: bool = False) -> torch.Tensor:
+    red = torch.empty((x.shape[0], groups, 2), dtype=torch.float32, device=x.device)
+    check(load().fdx_groupnorm_bwd(ctypes.byref(act(x, "x")), ctypes.byref(act(dy, "dy")),
+                                   ctypes.c_int(groups), ptr(stats), ptr(gamma), ptr(beta),
+                                   ctypes.c_float(eps), ctypes.c_int(1 if silu else 0), ptr(red),
+                                   ptr(dgamma), ptr(dbeta), ctypes.byref(act(dx, "dx")),
+                                   ctypes.c_int(1 if accumulate else 0), stream_ptr()),
+          "groupnorm_bwd")
+    return dx
+
+
+def rmsnorm_fwd(x, scale, eps: float, out=None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    check(load().fdx_rmsnorm_fwd(ctypes.byref(act(x, "x")), ptr(scale), ctypes.c_float(eps),
+                                 ctypes.byref(act(out, "out")), stream_ptr()), "rmsnorm_fwd")
+    return out
+
+
+def rmsnorm_bwd(x, dy, scale, eps, dx, dscale, accumulate: bool = False) -> torch.Tensor:
+    check(load().fdx_rmsnorm_bwd(ctypes.byref(act(x, "x")), ctypes.byref(act(dy, "dy")), ptr(scale),
+                                 ctypes.c_float(eps), ctypes.byref(act(dx, "dx")),
+                                 ctypes.c_int(1 if accumulate else 0), ptr(dscale), stream_ptr()),
+          "rmsnorm_bwd")
+    return dx
+
+
+# --------------------------------------------------------------------------- streaming
+TARGET_X0, TARGET_EPS, TARGET_V = 0, 1, 2
+
+
+def diffuse_forward(x0: torch.Tensor, eps: torch.Tensor, alpha, sigma, c_in, normalize: bool,
+                    target_kind: int):
+    """-> (x_t f32, target f32, model_in bf16); x0 may be uint8 or f32, shape (B, ...)."""
+    B = x0.shape[0]
+    E = x0.numel() // B
+    assert x0.is_contiguous() and eps.is_contiguous() and eps.dtype == torch.float32
+    assert x0.dtype in (torch.uint8, torch.float32)
+    x_t = torch.empty(tuple(x0.shape), dtype=torch.float32, device=x0.device)
+    target = torch.empty_like(x_t)
+    model_in = torch.empty(tuple(x0.shape), dtype=torch.bfloat16, device=x0.device)
+    check(load().fdx_diffuse_forward(ptr(x0), ctypes.c_int(1 if x0.dtype == torch.uint8 else 0),
+                                     ptr(eps), ptr(_f32c(alpha)), ptr(_f32c(sigma)), ptr(_f32c(c_in)),
+                                     ctypes.c_int(B), ctypes.c_longlong(E),
+                                     ctypes.c_int(1 if normalize else 0), ctypes.c_int(target_kind),
+                                     ptr(x_t), ptr(target), ptr(model_in), stream_ptr()),
+          "diffuse_forward")
+    return x_t, target, model_in
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.reshape(-1)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
+def loss_fwd_bwd(F: torch.Tensor, x_t, target, c_out, c_skip, weight, want_grad: bool = True):
+    """-> (loss scalar tensor f32[1], dF f32 or None)."""
+    B = F.shape[0]
+    E = F.numel() // B
+    loss = torch.empty(1, dtype=torch.float32, device=F.device)
+    dF = torch.empty_like(F) if want_grad else None
+    check(load().fdx_loss_fwd_bwd(ptr(F), ptr(x_t), ptr(target), ptr(_f32c(c_out)), ptr(_f32c(c_skip)),
+                                  ptr(_f32c(weight)), ctypes.c_int(B), ctypes.c_longlong(E), ptr(loss),
+                                  ptr(dF), stream_ptr()), "loss_fwd_bwd")
+    return loss, dF
+
+
+def affine_combine(inputs, coef1: torch.Tensor, coef2: Optional[torch.Tensor] = None,
+                   want_out1: bool = True, bf16_scale: Optional[torch.Tensor] = None,
+                   want_bf16: bool = False, clip=None):
+    """out1 = sum_i coef1[i,b]*in_i; out2 = sum_i coef2[i,b]*in_i; bf16 = bf16(out1*scale[b])."""
+    n_in = len(inputs)
+    x = inputs[0]
+    B = x.shape[0]
+    E = x.numel() // B
+    for t in inputs:
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.shape == x.shape
+    coef1 = coef1.to(torch.float32).contiguous()
+    assert coef1.shape == (n_in, B), (coef1.shape, n_in, B)
+    if coef2 is not None:
+        coef2 = coef2.to(torch.float32).contiguous()
+    arr = (ctypes.c_void_p * n_in)(*[t.data_ptr() for t in inputs])
+    out1 = torch.empty_like(x) if want_out1 else None
+    out2 = torch.empty_like(x) if coef2 is not None else None
+    outb = torch.empty(tuple(x.shape), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    lo, hi = (clip if clip is not None else (0.0, 0.0))
+    check(load().fdx_affine_combine(ctypes.c_int(n_in), arr, ptr(coef1), ptr(coef2),
+                                    ptr(_f32c(bf16_scale)) if bf16_scale is not None else ptr(None),
+                                    ctypes.c_int(B), ctypes.c_longlong(E), ptr(out1), ptr(out2),
+                                    ptr(outb), ctypes.c_int(1 if clip is not None else 0),
+                                    ctypes.c_float(lo), ctypes.c_float(hi), stream_ptr()),
+          "affine_combine")
+    return out1, out2, outb
+
+
+def adamw_ema_step(p, g, m, v, ema, shadow, lr, b1, b2, eps, weight_decay, step, ema_decay,
+                   grad_scale: float = 1.0, gnorm_sq=None, clip_norm: float = 0.0):
+    check(load().fdx_adamw_ema_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(shadow),
+                                    ctypes.c_longlong(p.numel()), ctypes.c_float(lr),
+                                    ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps),
+                                    ctypes.c_float(weight_decay), ctypes.c_int(step),
+                                    ctypes.c_float(ema_decay), ctypes.c_float(grad_scale),
+                                    ptr(gnorm_sq), ctypes.c_float(clip_norm), stream_ptr()),
+          "adamw_ema_step")
+
+
+def sumsq(g: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(1, dtype=torch.float32, device=g.device)
+    check(load().fdx_sumsq(ptr(g), ctypes.c_longlong(g.numel()), ptr(out), stream_ptr()), "sumsq")
+    return out
+
+
+def cast_f32_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    if dst is None:
+        dst = torch.empty(tuple(src.shape), dtype=torch.bfloat16, device=src.device)
+    check(load().fdx_cast_f32_bf16(ptr(src), ptr(dst), ctypes.c_longlong(src.numel()), stream_ptr()),
+          "cast_f32_bf16")
+    return dst
+
+
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+    check(load().fdx_upsample2x(ctypes.byref(act(x, "x")), ctypes.byref(act(out, "out")), stream_ptr()),
+          "upsample2x")
+    return out
+
+
+def upsample2x_bwd(dy: torch.Tensor, dx: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+    check(load().fdx_upsample2x_bwd(ctypes.byref(act(dy, "dy")), ctypes.byref(act(dx, "dx")),
+                                    ctypes.c_int(1 if accumulate else 0), stream_ptr()),
+          "upsample2x_bwd")
+    return dx
+
+
+def act_add(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    check(load().fdx_act_add(ctypes.byref(act(a, "a")), ctypes.byref(act(b, "b")),
+                             ctypes.byref(act(out, "out")), stream_ptr()), "act_add")
+    return out
+
+
+def colsum(x: torch.Tensor, per_image: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        shape = (x.shape[0], x.shape[-1]) if per_image else (x.shape[-1],)
+        out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    check(load().fdx_colsum(ctypes.byref(act(x, "x")), ptr(out), ctypes.c_int(1 if per_image else 0),
+                            stream_ptr()), "colsum")
+    return out
+
+
+# --------------------------------------------------------------------------- 3-channel convs
+def conv_in_fwd(x_bf16: torch.Tensor, w: torch.Tensor, bias, out: torch.Tensor) -> torch.Tensor:
+    n, h, w_, c = x_bf16.shape
+    assert c == 3 and x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous()
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    check(load().fdx_conv_in_fwd(ptr(x_bf16), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w_),
+                                 ptr(w), ptr(bias), ctypes.byref(act(out, "out")), stream_ptr()),
+          "conv_in_fwd")
+    return out
+
+
+def conv_in_wgrad(x_bf16, dy, dw, dbias):
+    check(load().fdx_conv_in_wgrad(ptr(x_bf16), ctypes.byref(act(dy, "dy")), ptr(dw), ptr(dbias),
+                                   stream_ptr()), "conv_in_wgrad")
+
+
+def conv_out_fwd(x: torch.Tensor, w: torch.Tensor, bias) -> torch.Tensor:
+    n, h, w_, c = x.shape
+    y = torch.empty((n, h, w_, 3), dtype=torch.float32, device=x.device)
+    check(load().fdx_conv_out_fwd(ctypes.byref(act(x, "x")), ptr(w), ptr(bias), ptr(y), stream_ptr()),
+          "conv_out_fwd")
+    return y
+
+
+def conv_out_dgrad(dF: torch.Tensor, w: torch.Tensor, dx: torch.Tensor) -> torch.Tensor:
+    check(load().fdx_conv_out_dgrad(ptr(dF), ptr(w), ctypes.byref(act(dx, "dx")), stream_ptr()),
+          "conv_out_dgrad")
+    return dx
+
+
+def conv_out_wgrad(x, dF, dw, dbias):
+    check(load().fdx_conv_out_wgrad(ctypes.byref(act(x, "x")), ptr(dF), ptr(dw), ptr(dbias),
+                                    stream_ptr()), "conv_out_wgrad")
+
+
+# --------------------------------------------------------------------------- temb / softmax
+def time_embed_fwd(t, freqs, W1, b1, W2, b2):
+    B, D = t.shape[0], W1.shape[0]
+    dev = t.device
+    four = torch.empty((B, D), dtype=torch.float32, device=dev)
+    h1 = torch.empty_like(four)
+    h2 = torch.empty_like(four)
+    emb = torch.empty_like(four)
+    emb16 = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
+    check(load().fdx_time_embed_fwd(ptr(_f32c(t)), ptr(freqs), ptr(W1), ptr(b1), ptr(W2), ptr(b2),
+                                    ctypes.c_int(B), ctypes.c_int(D), ptr(four), ptr(h1), ptr(h2),
+                                    ptr(emb), ptr(emb16), stream_ptr()), "time_embed_fwd")
+    return emb, emb16, (four, h1, h2)
+
+
+def time_embed_bwd(demb, saved, W2, dW1, db1, dW2, db2):
+    four, h1, h2 = saved
+    B, D = demb.shape
+    ws1 = torch.empty_like(demb)
+    ws2 = torch.empty_like(demb)
+    check(load().fdx_time_embed_bwd(ptr(demb), ptr(four), ptr(h1), ptr(h2), ptr(W2), ctypes.c_int(B),
+                                    ctypes.c_int(D), ptr(ws1), ptr(ws2), ptr(dW1), ptr(db1), ptr(dW2),
+                                    ptr(db2), stream_ptr()), "time_embed_bwd")
+
+
+def softmax_fwd(S: torch.Tensor) -> torch.Tensor:
+    L = S.shape[-1]
+    P = torch.empty(tuple(S.shape), dtype=torch.bfloat16, device=S.device)
+    check(load().fdx_softmax_fwd(ptr(S), ctypes.c_longlong(S.numel() // L), ctypes.c_int(L), ptr(P),
+                                 stream_ptr()), "softmax_fwd")
+    return P
+
+
+def softmax_bwd(P: torch.Tensor, dP: torch.Tensor, scale: float) -> torch.Tensor:
+    L = P.shape[-1]
+    dS = torch.empty(tuple(P.shape), dtype=torch.bfloat16, device=P.device)
+    check(load().fdx_softmax_bwd(ptr(P), ptr(dP), ctypes.c_longlong(P.numel() // L), ctypes.c_int(L),
+                                 ctypes.c_float(scale), ptr(dS), stream_ptr()), "softmax_bwd")
+    return dS

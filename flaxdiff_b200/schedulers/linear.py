@@ -1,0 +1,2 @@
+"""Alias of flaxdiff/schedulers/linear.py's module path; the implementation lives in .vp."""
+from .vp import *  # noqa: F401,F403

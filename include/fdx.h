@@ -73,6 +73,83 @@ typedef struct {
  * and the QK^T / PV / backward products of nn.dot_product_attention (attention.py:170-174). */
 int fdx_gemm(const fdx_gemm_desc* g, void* stream);
 
+/* ---- normalisation (HBM-bound; warp-shuffle + shared/global atomics reductions) ---- */
+/* nn.GroupNorm(groups, eps) statistics (models/common.py:273-281): stats[n][g] = (sum, sumsq), f32. */
+int fdx_groupnorm_stats(const fdx_act* x, int groups, float* stats, void* stream);
+/* y = silu?((x-mean)*rstd*gamma+beta) (models/common.py:286-288,310-312; simple_unet.py:209-210). */
+int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const float* gamma,
+                        const float* beta, float eps, int silu, const fdx_act* y, void* stream);
+/* Backward of the pair above. red: [n][g][2] f32 scratch; dgamma/dbeta ACCUMULATED. */
+int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
+                      const float* gamma, const float* beta, float eps, int silu, float* red,
+                      float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
+                      void* stream);
+/* nn.RMSNorm(eps) over channels (models/attention.py:325-326). C in {256,512,768,1024}. */
+int fdx_rmsnorm_fwd(const fdx_act* x, const float* scale, float eps, const fdx_act* y,
+                    void* stream);
+int fdx_rmsnorm_bwd(const fdx_act* x, const fdx_act* dy, const float* scale, float eps,
+                    const fdx_act* dx, int accumulate, float* dscale, void* stream);
+
+/* ---- diffusion step streaming kernels ------------------------------------------------ */
+/* (x-127.5)/127.5, x_t = alpha*x0 + sigma*eps, target, model input bf16(x_t*c_in)
+ * (trainer/general_diffusion_trainer.py:258,285-291; predictors/__init__.py:19-24).
+ * target_kind: 0 = x0, 1 = eps, 2 = v.  E = elements per sample. */
+int fdx_diffuse_forward(const void* x0, int x0_is_u8, const float* eps, const float* alpha,
+                        const float* sigma, const float* c_in, int B, long long E, int normalize,
+                        int target_kind, float* x_t, float* target, void* model_in_bf16,
+                        void* stream);
+/* pred = c_out*F + c_skip*x_t; loss = mean(0.5*(pred-target)^2*w); dF = dloss/dF
+ * (general_diffusion_trainer.py:295-302; predictors/__init__.py:84-91). */
+int fdx_loss_fwd_bwd(const float* F, const float* x_t, const float* target, const float* c_out,
+                     const float* c_skip, const float* weight, int B, long long E,
+                     float* loss_sum, float* dF, void* stream);
+/* out1 = sum_i coef1[i][b]*in_i ; out2 = sum_i coef2[i][b]*in_i ; out_bf16 = bf16(out1*scale[b]).
+ * One pass for x0/eps recovery, CFG mixing (samplers/common.py:93-96) and every sampler update
+ * (samplers/euler.py:8-18,39-56; heun_sampler.py:7-27; ddim.py:30-47; ddpm.py:6-15). */
+int fdx_affine_combine(int n_in, const float* const* inputs, const float* coef1, const float* coef2,
+                       const float* bf16_scale, int B, long long E, float* out1, float* out2,
+                       void* out_bf16, int clip, float clip_lo, float clip_hi, void* stream);
+/* optax adamw (training.py:598-608) + TrainState.apply_ema (trainer/diffusion_trainer.py:31-37)
+ * + bf16 shadow-weight refresh over one flat buffer; optional clip_by_global_norm. */
+int fdx_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16,
+                       long long n, float lr, float b1, float b2, float eps, float weight_decay,
+                       int step, float ema_decay, float grad_scale, const float* gnorm_sq,
+                       float clip_norm, void* stream);
+int fdx_sumsq(const float* g, long long n, float* out, void* stream);
+int fdx_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+/* jax.image.resize(nearest) x2 (models/common.py:214-215) and its adjoint. */
+int fdx_upsample2x(const fdx_act* x, const fdx_act* y, void* stream);
+int fdx_upsample2x_bwd(const fdx_act* dy, const fdx_act* dx, int accumulate, void* stream);
+int fdx_act_add(const fdx_act* a, const fdx_act* b, const fdx_act* out, void* stream);
+/* column sums over pixels: out[c] or out[n][c] (bias / timestep-vector gradients). */
+int fdx_colsum(const fdx_act* x, float* out, int per_image, void* stream);
+
+/* ---- 3-channel convolutions (CUDA cores) ----------------------------------------------- */
+/* conv_in 3->Cout (models/simple_unet.py:47-54): x bf16 [N,H,W,3] dense, w f32 HWIO. */
+int fdx_conv_in_fwd(const void* x_bf16, int N, int H, int W, const float* w_hwio,
+                    const float* bias, const fdx_act* y, void* stream);
+int fdx_conv_in_wgrad(const void* x_bf16, const fdx_act* dy, float* dw_hwio, float* dbias,
+                      void* stream);
+/* conv_out Cin->3 (models/simple_unet.py:212-221): y f32 [N,H,W,3] dense. */
+int fdx_conv_out_fwd(const fdx_act* x, const float* w_hwio, const float* bias, float* y_f32,
+                     void* stream);
+int fdx_conv_out_dgrad(const float* dF, const float* w_hwio, const fdx_act* dx, void* stream);
+int fdx_conv_out_wgrad(const fdx_act* x, const float* dF, float* dw_hwio, float* dbias,
+                       void* stream);
+
+/* ---- timestep embedding + softmax ------------------------------------------------------ */
+/* FourierEmbedding + TimeProjection (models/common.py:97-124), f32; saves four/h1/h2 for bwd. */
+int fdx_time_embed_fwd(const float* t, const float* freqs, const float* W1, const float* b1,
+                       const float* W2, const float* b2, int B, int D, float* four, float* h1,
+                       float* h2, float* emb, void* emb_bf16, void* stream);
+int fdx_time_embed_bwd(const float* demb, const float* four, const float* h1, const float* h2,
+                       const float* W2, int B, int D, float* dh1_ws, float* dh2_ws, float* dW1,
+                       float* db1, float* dW2, float* db2, void* stream);
+/* softmax of nn.dot_product_attention (models/attention.py:170-174): S f32 -> P bf16. */
+int fdx_softmax_fwd(const float* S, long long rows, int L, void* P_bf16, void* stream);
+int fdx_softmax_bwd(const void* P_bf16, const float* dP, long long rows, int L, float scale,
+                    void* dS_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
