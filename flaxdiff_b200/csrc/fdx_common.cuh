@@ -36,7 +36,12 @@ int fdx_check_cuda(cudaError_t e, const char* what);
     }                                                         \
   } while (0)
 
-#define FDX_LAUNCH_CHECK() FDX_CUDA(cudaPeekAtLastError())
+void fdx_count_launch();
+#define FDX_LAUNCH_CHECK()                 \
+  do {                                     \
+    fdx_count_launch();                    \
+    FDX_CUDA(cudaPeekAtLastError());       \
+  } while (0)
 
 // Encode a tiled TMA descriptor (bf16) through the driver entry point.
 // rank <= 5, dims/strides innermost first; strides in BYTES for dims 1..rank-1.

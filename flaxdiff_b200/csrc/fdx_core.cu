@@ -13,7 +13,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 std::once_flag g_encode_once;
 int g_sms = -1;
+unsigned long long g_launches = 0;
 }  // namespace
+
+void fdx_count_launch() { ++g_launches; }
 
 void fdx_set_error(const char* fmt, ...) {
   va_list ap;
@@ -94,4 +97,5 @@ extern "C" {
 const char* fdx_last_error(void) { return g_err; }
 int fdx_version(void) { return 100; }
 int fdx_device_sm_count(void) { return fdx_num_sms(); }
+unsigned long long fdx_launch_count(void) { return g_launches; }
 }

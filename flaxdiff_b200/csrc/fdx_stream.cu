@@ -166,7 +166,10 @@ __global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict_
                                  float* __restrict__ ema, __nv_bfloat16* __restrict__ shadow,
                                  long long n, float lr, float b1, float b2, float eps, float wd,
                                  float bc1, float bc2, float ema_decay, float gscale,
-                                 const float* __restrict__ gnorm_sq, float clip_norm) {
+                                 const float* __restrict__ gnorm_sq, float clip_norm,
+                                 const float* __restrict__ dyn) {
+  // dyn (device) = {lr, 1-b1^t, 1-b2^t}: lets a CUDA graph replay the step with fresh values
+  if (dyn) { lr = dyn[0]; bc1 = dyn[1]; bc2 = dyn[2]; }
   float gs = gscale;
   if (gnorm_sq && clip_norm > 0.f) {
     // optax.clip_by_global_norm: g * min(1, clip / ||g||)
@@ -410,14 +413,14 @@ int fdx_affine_combine(int n_in, const float* const* inputs, const float* coef1,
 int fdx_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16,
                        long long n, float lr, float b1, float b2, float eps, float weight_decay,
                        int step, float ema_decay, float grad_scale, const float* gnorm_sq,
-                       float clip_norm, void* stream) {
+                       float clip_norm, const float* dyn_lr_bc, void* stream) {
   FDX_REQUIRE(p && g && m && v && ema, "adamw_ema: null pointer");
   FDX_REQUIRE(n > 0 && n % 4 == 0, "adamw_ema: n=%lld must be a multiple of 4 (pad the flat buffer)", n);
   FDX_REQUIRE(step >= 1, "adamw_ema: step counts from 1");
   const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
   adamw_ema_kernel<<<stream_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
       p, g, m, v, ema, (__nv_bfloat16*)shadow_bf16, n, lr, b1, b2, eps, weight_decay, bc1, bc2,
-      ema_decay, grad_scale, gnorm_sq, clip_norm);
+      ema_decay, grad_scale, gnorm_sq, clip_norm, dyn_lr_bc);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

@@ -1,0 +1,122 @@
+"""Conditioning-input configuration (API of flaxdiff/inputs/__init__.py:15-172).
+
+Only the contract the samplers / trainer need is kept: which batch key feeds which model
+kwarg, the cached unconditional ("null") embedding, and the per-sample null mixing used for
+classifier-free-guidance training.  The CLIP text encoder itself is out of scope (BASELINE
+config 4 uses frozen random text embeddings): `RandomEmbeddingEncoder` stands in for it.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+
+class ConditioningEncoder:
+    """Maps raw conditioning (e.g. strings) to an embedding tensor (B, T, D)."""
+    key = "text"
+
+    def __call__(self, data) -> torch.Tensor:
+        raise NotImplementedError
+
+    def encode_from_tokens(self, tokens) -> torch.Tensor:
+        raise NotImplementedError
+
+    def serialize(self) -> dict:
+        return {}
+
+
+class RandomEmbeddingEncoder(ConditioningEncoder):
+    """Frozen random embeddings keyed by hash of the input (stand-in for CLIPTextEncoder,
+    flaxdiff/inputs/encoders.py:61-94)."""
+
+    def __init__(self, seq_len: int = 77, features: int = 768, key: str = "text", device=None, seed: int = 0):
+        self.seq_len, self.features, self.key, self.seed = seq_len, features, key, seed
+        self.device = device
+
+    def _one(self, item) -> torch.Tensor:
+        g = torch.Generator()
+        g.manual_seed((hash(str(item)) ^ self.seed) & 0x7FFFFFFF)
+        return torch.randn(self.seq_len, self.features, generator=g)
+
+    def __call__(self, data) -> torch.Tensor:
+        if isinstance(data, torch.Tensor):
+            return data
+        out = torch.stack([self._one(d) for d in data])
+        return out.to(self.device) if self.device is not None else out
+
+    def encode_from_tokens(self, tokens):
+        return self(tokens)
+
+    def serialize(self):
+        return {"seq_len": self.seq_len, "features": self.features, "seed": self.seed}
+
+
+@dataclass
+class ConditionalInputConfig:
+    encoder: ConditioningEncoder
+    conditioning_data_key: str = None
+    pretokenized: bool = False
+    unconditional_input: Any = None
+    model_key_override: Optional[str] = None
+
+    def __post_init__(self):
+        null = self.unconditional_input if self.unconditional_input is not None else ""
+        self._uncond = self.encoder([null])
+
+    def __call__(self, batch_data):
+        key = self.conditioning_data_key if self.conditioning_data_key else self.encoder.key
+        if self.pretokenized:
+            return self.encoder.encode_from_tokens(batch_data[key])
+        return self.encoder(batch_data[key])
+
+    def get_unconditional(self):
+        return self._uncond
+
+    def serialize(self):
+        return {"encoder": self.encoder.serialize(), "encoder_key": self.encoder.key,
+                "conditioning_data_key": self.conditioning_data_key,
+                "unconditional_input": self.unconditional_input,
+                "model_key_override": self.model_key_override}
+
+
+@dataclass
+class DiffusionInputConfig:
+    sample_data_key: str
+    sample_data_shape: Tuple[int, ...]
+    conditions: List[ConditionalInputConfig] = field(default_factory=list)
+
+    def get_input_shapes(self, autoencoder=None, sample_model_key: str = 'x',
+                         time_embeddings_model_key: str = 'temb') -> Dict[str, Tuple[int, ...]]:
+        if len(self.sample_data_shape) == 3:
+            H, W, C = self.sample_data_shape
+        elif len(self.sample_data_shape) == 4:
+            _, H, W, C = self.sample_data_shape
+        else:
+            raise ValueError(f"Unsupported shape for sample data {self.sample_data_shape}")
+        shapes = {sample_model_key: (H, W, C), time_embeddings_model_key: ()}
+        for cond in self.conditions:
+            key = cond.model_key_override if cond.model_key_override else cond.encoder.key
+            shapes[key] = tuple(cond.get_unconditional()[0].shape)
+        return shapes
+
+    def get_unconditionals(self):
+        return [c.get_unconditional() for c in self.conditions]
+
+    def process_conditioning(self, batch_data, uncond_mask: Optional[torch.Tensor] = None):
+        """Per-sample null mixing (inputs/__init__.py:123-146)."""
+        results = []
+        for cond in self.conditions:
+            emb = cond(batch_data)
+            if uncond_mask is not None:
+                assert len(uncond_mask) == len(emb), "Unconditional mask length must match the batch size."
+                null = cond.get_unconditional().to(emb.device).expand_as(emb)
+                mask = uncond_mask.to(emb.device).reshape([len(uncond_mask)] + [1] * (emb.dim() - 1))
+                emb = torch.where(mask.bool(), null, emb)
+            results.append(emb)
+        return results
+
+    def serialize(self):
+        return {"sample_data_key": self.sample_data_key, "sample_data_shape": self.sample_data_shape,
+                "conditions": [c.serialize() for c in self.conditions]}

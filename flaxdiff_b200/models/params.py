@@ -96,6 +96,13 @@ class FlatParams(dict):
         self.shadow()
         return self._shadow_flat
 
+    def shadow_flat_noupdate(self) -> torch.Tensor:
+        """The shadow buffer itself (allocated if needed) without refreshing it."""
+        if self._shadow is None:
+            self._shadow_flat = torch.empty(self.layout.total, dtype=torch.bfloat16, device=self.flat.device)
+            self._shadow = self.layout.views(self._shadow_flat)
+        return self._shadow_flat
+
     def mark_shadow_fresh(self):
         """The fused optimiser kernel refreshed the shadow itself."""
         self._shadow_version = self.flat._version

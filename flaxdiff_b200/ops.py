@@ -209,13 +209,13 @@ def affine_combine(inputs, coef1: torch.Tensor, coef2: Optional[torch.Tensor] = 
 
 
 def adamw_ema_step(p, g, m, v, ema, shadow, lr, b1, b2, eps, weight_decay, step, ema_decay,
-                   grad_scale: float = 1.0, gnorm_sq=None, clip_norm: float = 0.0):
+                   grad_scale: float = 1.0, gnorm_sq=None, clip_norm: float = 0.0, dyn=None):
     check(load().fdx_adamw_ema_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(shadow),
                                     ctypes.c_longlong(p.numel()), ctypes.c_float(lr),
                                     ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps),
                                     ctypes.c_float(weight_decay), ctypes.c_int(step),
                                     ctypes.c_float(ema_decay), ctypes.c_float(grad_scale),
-                                    ptr(gnorm_sq), ctypes.c_float(clip_norm), stream_ptr()),
+                                    ptr(gnorm_sq), ctypes.c_float(clip_norm), ptr(dyn), stream_ptr()),
           "adamw_ema_step")
 
 

@@ -1,0 +1,2 @@
+"""Alias of flaxdiff/samplers/ddpm.py's module path; the implementation lives in .steps."""
+from .steps import *  # noqa: F401,F403

@@ -37,6 +37,8 @@ typedef struct {
 const char* fdx_last_error(void);
 int fdx_version(void);
 int fdx_device_sm_count(void);
+/* number of libfdx kernels launched (or captured into a CUDA graph) by this process so far */
+unsigned long long fdx_launch_count(void);
 
 /* ---- tensor-core contractions (tcgen05 + TMA + TMEM) ------------------------- */
 /* flax nn.Conv 3x3 SAME, stride 1 or 2 (models/common.py:166-172, 237-244).
@@ -114,7 +116,8 @@ int fdx_affine_combine(int n_in, const float* const* inputs, const float* coef1,
 int fdx_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16,
                        long long n, float lr, float b1, float b2, float eps, float weight_decay,
                        int step, float ema_decay, float grad_scale, const float* gnorm_sq,
-                       float clip_norm, void* stream);
+                       float clip_norm, const float* dyn_lr_bc /* device {lr,1-b1^t,1-b2^t} or NULL */,
+                       void* stream);
 int fdx_sumsq(const float* g, long long n, float* out, void* stream);
 int fdx_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 /* jax.image.resize(nearest) x2 (models/common.py:214-215) and its adjoint. */

@@ -1,0 +1,120 @@
+"""Host-side logic of the drop-in surface (schedulers / predictors coefficient algebra / sampler
+step sequences) against the NumPy oracle, on CPU tensors.  Integer timestep work is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from flaxdiff_b200 import predictors as P
+from flaxdiff_b200 import samplers as S
+from flaxdiff_b200 import schedulers as sc
+from oracle import diffusion_ref as R
+
+CPU = torch.device("cpu")
+
+
+def test_linear_schedule_tables_match_oracle():
+    s = sc.LinearNoiseSchedule(1000).to(CPU)
+    t = R.linear_tables(1000)
+    for name in ("alpha_cumprod", "sqrt_alpha_cumprod", "sqrt_one_minus_alpha_cumprod", "posterior_variance",
+                 "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2", "p2_loss_weights"):
+        np.testing.assert_allclose(getattr(s, name).numpy(), t[name], rtol=3e-6, atol=0, err_msg=name)
+
+
+def test_discrete_gather_indices_bit_exact():
+    s = sc.LinearNoiseSchedule(1000).to(CPU)
+    steps = torch.tensor([0, 1, 999, 1000, 1500, 12.9, 500.99])
+    idx = s._index(steps).numpy()
+    assert idx.tolist() == R.discrete_index(steps.numpy()).tolist() == [0, 1, 999, 999, 999, 12, 500]
+    a, sg = s.get_rates(steps, shape=(-1,))
+    t = R.linear_tables(1000)
+    np.testing.assert_array_equal(a.numpy(), s.sqrt_alpha_cumprod.numpy()[idx])
+    np.testing.assert_allclose(sg.numpy(), t["sqrt_one_minus_alpha_cumprod"][idx], rtol=3e-6)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 18, 30, 50, 64, 100, 200, 333, 999, 1000])
+def test_get_steps_bit_exact(n):
+    smp = S.EulerSampler(None, sc.KarrasVENoiseScheduler(1), P.KarrasPredictionTransform(0.5), None)
+    got = smp.get_steps(1000, 0, n)
+    want = R.get_steps_linear(1000, 0, n)
+    assert got.dtype == np.int16
+    np.testing.assert_array_equal(got, want)
+    assert got[0] == 1000 or n == 1
+    assert got[-1] == 0 or n == 1
+
+
+def test_karras_and_edm_schedules_match_oracle():
+    k = sc.KarrasVENoiseScheduler(1, sigma_max=80, rho=7, sigma_data=0.5).to(CPU)
+    t = torch.tensor([1.0, 0.999, 0.75, 0.5, 0.25, 0.001, 0.0, 1.5, -0.2])
+    np.testing.assert_allclose(k.get_sigmas(t).numpy(), R.karras_sigma(t.numpy()), rtol=2e-5)
+    np.testing.assert_allclose(k.get_weights(t, (-1,)).numpy(), R.karras_weight(R.karras_sigma(t.numpy())), rtol=1e-4)
+    np.testing.assert_allclose(k.transform_inputs(None, t)[1].numpy(), R.karras_model_time(R.karras_sigma(t.numpy())),
+                               rtol=1e-4, atol=1e-6)
+    e = sc.EDMNoiseScheduler(1, sigma_max=80, rho=7, sigma_data=0.5).to(CPU)
+    tn = torch.tensor([-2.0, -0.3, 0.0, 1.0, 2.5])
+    np.testing.assert_allclose(e.get_sigmas(tn).numpy(), R.edm_sigma(tn.numpy()), rtol=2e-6)
+    a, s = e.get_rates(tn)
+    assert a.shape == (5, 1, 1, 1) and torch.all(a == 1)
+    # inverse map
+    np.testing.assert_allclose(k.get_timesteps(k.get_sigmas(t[:7])).numpy(), t[:7].numpy(), atol=2e-3)
+
+
+def _apply(coefs, x, F):
+    p, q, r, u = [c.numpy().reshape(-1, 1, 1, 1) for c in coefs]
+    return p * x + q * F, r * x + u * F
+
+
+@pytest.mark.parametrize("kind,cls", [("epsilon", P.EpsilonPredictionTransform), ("direct", P.DirectPredictionTransform),
+                                      ("v", P.VPredictionTransform), ("karras", P.KarrasPredictionTransform)])
+def test_prediction_transform_coefficients(kind, cls):
+    rng = np.random.default_rng(1)
+    B = 5
+    x = rng.standard_normal((B, 4, 4, 3), dtype=np.float32)
+    F = rng.standard_normal((B, 4, 4, 3), dtype=np.float32)
+    if kind == "karras":
+        alpha = np.ones(B, dtype=np.float32)
+        sigma = np.array([0.002, 0.3, 1.0, 7.0, 80.0], dtype=np.float32)
+    else:
+        sigma = np.array([0.05, 0.3, 0.6, 0.9, 0.999], dtype=np.float32)
+        alpha = np.sqrt(1 - sigma ** 2).astype(np.float32)
+    tr = cls()
+    rates = (torch.from_numpy(alpha).reshape(-1, 1, 1, 1), torch.from_numpy(sigma).reshape(-1, 1, 1, 1))
+    x0, eps = _apply(tr.x0_eps_coeffs(rates), x, F)
+    w0, we = R.x0_eps_from_output(kind, x, F, alpha, sigma)
+    np.testing.assert_allclose(x0, w0, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(eps, we, rtol=2e-4, atol=2e-4)
+    if kind == "karras":
+        c_in, c_out, c_skip = R.karras_coeffs(sigma)
+        np.testing.assert_allclose(tr.get_input_scale(rates).numpy().reshape(-1), c_in, rtol=1e-6)
+        lo, ls = tr.loss_coeffs(rates)
+        np.testing.assert_allclose(lo.numpy(), c_out, rtol=1e-6)
+        np.testing.assert_allclose(ls.numpy(), c_skip, rtol=1e-6)
+
+
+def test_unet_param_tree_matches_reference_checkpoints():
+    """Names of the flax parameter tree vs real FlaxDiff checkpoints (tests/golden/param_names.json,
+    generated from /root/reference/pretrained/*/_METADATA by make_param_name_fixture.py)."""
+    import json
+    import os
+
+    from flaxdiff_b200.models.simple_unet import Unet
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "param_names.json")))
+    ours4 = set(n for n, _ in Unet(attention_configs=(None,) * 4, named_norms=True).param_specs())
+    old = [v for k, v in d.items() if k.startswith("cosine trained old")][0]
+    ref_old = set(n for n in old if "attention" not in n and "middle_conv" not in n)
+    assert ref_old <= ours4, sorted(ref_old - ours4)[:5]
+    assert ours4 - ref_old <= {"middle_res1_0/residual_conv/conv/bias", "middle_res1_0/residual_conv/conv/kernel"}
+    cond = [v for k, v in d.items() if k.startswith("EDM + Conditional")][0]
+    assert ours4 <= set(cond)
+    ours5 = set(n for n, _ in Unet(feature_depths=(64, 64, 128, 256, 512), attention_configs=(None,) * 5,
+                                  named_norms=True).param_specs())
+    ref5 = set(n for n in cond if "attention" not in n)
+    assert ref5 == ours5, (sorted(ref5 - ours5)[:5], sorted(ours5 - ref5)[:5])   # notebook config [64,64,128,256,512]
+    # attention parameter leaf names of the current code path (Attention/Attention2/...) share the leaves
+    attn = set(n.split("/")[-2] for n in cond if "attention" in n and n.endswith("kernel"))
+    assert attn == {"to_q", "to_k", "to_v", "to_out_0"}
+
+
+def test_unet_param_counts():
+    from flaxdiff_b200.models.simple_unet import Unet
+    assert Unet(attention_configs=(None,) * 4).layout().num_params == 32040707          # 32.04 M (SURVEY $8d)
+    assert Unet(attention_configs=(None, None, None, {"heads": 8})).layout().num_params == 34401283   # 34.40 M
