@@ -32,6 +32,28 @@ WORKLOADS = {
 }
 
 
+def usable_cores() -> int:
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the whole host inside a container and oversubscribes the thread pool)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        n = os.cpu_count() or 1
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = min(n, max(1, int(int(q[0]) / int(q[1]))))
+    except Exception:  # noqa: BLE001
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, min(n, 64))
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -100,7 +122,7 @@ def run_reference(args):
     from flaxdiff_b200.models.simple_unet import Unet
     from oracle import train_ref
     res, _, acfg, desc = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     B = args.ref_batch
     model = Unet(attention_configs=acfg)
@@ -145,6 +167,12 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ this repo
+def log(msg):
+    if os.environ.get("FDX_BENCH_VERBOSE"):
+        sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n")
+        sys.stderr.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,6 +188,10 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=16)
     ap.add_argument("--ref-max-steps", type=int, default=3)
     args = ap.parse_args()
+    import faulthandler
+    faulthandler.enable()
+    if os.environ.get("FDX_BENCH_WATCHDOG"):
+        faulthandler.dump_traceback_later(int(os.environ["FDX_BENCH_WATCHDOG"]), repeat=True, file=sys.stderr)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -207,10 +239,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log('trainer built')
     # ---- device-resident timing (value) -------------------------------------------------------
     l0 = lib.fdx_launch_count()
     for i in range(args.warmup):
         trainer.state, loss, trainer.rngstate = step_fn(trainer.state, trainer.rngstate, {"image": dev_batch}, rank)
+        torch.cuda.synchronize()
+        log(f'warmup step {i} done')
     torch.cuda.synchronize()
     launches_eager_plus_capture = lib.fdx_launch_count() - l0
     # launches per step: measure one more eager (non-captured) replay-equivalent by counting a capture
@@ -224,6 +259,7 @@ def main():
     e1.record()
     sync_all()
     ms_dev = e0.elapsed_time(e1) / args.steps
+    log(f'device-resident: {ms_dev:.2f} ms/step')
     # ---- end-to-end timing: pinned host batch -> device each step, loss read back each step -----
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -237,6 +273,7 @@ def main():
     sync_all()
     clk = clocks.stop()
     ms_e2e = e2.elapsed_time(e3) / args.steps
+    log(f'e2e: {ms_e2e:.2f} ms/step')
     t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -251,7 +288,9 @@ def main():
     launches_per_step = int(lib.fdx_launch_count() - l1) + 1   # + fused AdamW/EMA kernel
 
     # ---- tensor-core engine time inside one step (roofline of the dominant kernel) -------------
+    log('counted launches')
     tc_ms, tc_calls = profile_tc(trainer, dev_batch, noise, tt)
+    log(f'tc profile: {tc_ms:.2f} ms in {tc_calls} launches')
     hbm, tf_burst, tf_sust, src = load_peaks()
     step_tflop = 3 * fwd_gflop * B / 1e3
     tc_tflops = step_tflop / (tc_ms / 1e3) if tc_ms > 0 else 0.0
@@ -275,6 +314,7 @@ def main():
         if world > 1:
             dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         ms_s = float(ts[0])
+        log(f'sampling: {ms_s:.1f} ms')
         sample = {"sampler": "EulerSampler", "diffusion_steps": n_s, "batch_per_gpu": B,
                   "denoise_steps_per_sec": n_s / (ms_s / 1e3),
                   "image_steps_per_sec": world * B * n_s / (ms_s / 1e3),
@@ -349,7 +389,7 @@ def cpu_baseline(args, model, res, acfg):
     """The oracle train step timed on the host cores on a bounded sample (rank 0, N=1 only)."""
     import torch
     from oracle import train_ref
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     B = args.ref_batch
     fp = model.init(4, device=torch.device("cpu"))

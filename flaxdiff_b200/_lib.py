@@ -66,8 +66,39 @@ def load() -> ctypes.CDLL:
             "or `make -C flaxdiff_b200/csrc`. flaxdiff_b200 has no CPU fallback.")
     lib = ctypes.CDLL(_LIB_PATH)
     lib.fdx_last_error.restype = ctypes.c_char_p
+    if os.environ.get("FDX_TRACE"):
+        lib = _TracingLib(lib)
     _lib = lib
     return lib
+
+
+class _TracingLib:
+    """Debug aid (FDX_TRACE=1): log every C-ABI call to stderr and synchronise after it, so a hung
+    or faulting kernel is attributed to the entry point that launched it."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._n = 0
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith("fdx_") or name in ("fdx_last_error", "fdx_launch_count", "fdx_version"):
+            return fn
+
+        def traced(*args):
+            import sys
+            import time
+            self._n += 1
+            t0 = time.time()
+            sys.stderr.write(f"[fdx-trace {self._n}] {name} ...")
+            sys.stderr.flush()
+            r = fn(*args)
+            if not torch.cuda.is_current_stream_capturing():
+                torch.cuda.synchronize()
+            sys.stderr.write(f" rc={r} {1e3 * (time.time() - t0):.2f} ms\n")
+            sys.stderr.flush()
+            return r
+        return traced
 
 
 def check(status: int, what: str = "") -> None:

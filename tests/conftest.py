@@ -8,8 +8,27 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _usable_cores() -> int:
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        n = os.cpu_count() or 1
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = min(n, max(1, int(int(q[0]) / int(q[1]))))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, min(n, 32))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    try:
+        import torch
+        torch.set_num_threads(_usable_cores())   # os.cpu_count() over-reports inside a cgroup
+    except Exception:  # noqa: BLE001
+        pass
 
 
 def pytest_collection_modifyitems(config, items):

@@ -1,0 +1,84 @@
+"""Per-layer microbenchmark of the tcgen05 engine on the UNet's distinct contraction shapes
+(SURVEY.md Appendix D).  Run under gpurun; prints one line per (shape, pass) with TFLOP/s.
+    python tests/gpu_bench_layers.py [64|256] [batch]
+"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from flaxdiff_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda")
+
+# (out_res_div, Cin, Cout, stride) with res_div relative to the full resolution
+SHAPES = [
+    (1, 64, 64, 1), (1, 128, 64, 1), (1, 320, 64, 1), (1, 128, 256, 1),
+    (2, 64, 64, 1), (2, 128, 128, 1), (2, 192, 128, 1), (2, 576, 128, 1), (2, 256, 512, 1),
+    (4, 128, 128, 1), (4, 256, 256, 1), (4, 192, 256, 1), (4, 384, 256, 1), (4, 512, 64, 1),
+    (8, 256, 256, 1), (8, 256, 512, 1), (8, 512, 512, 1), (8, 768, 512, 1),
+    (2, 64, 64, 2), (4, 64, 128, 2), (8, 128, 256, 2),
+]
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    res = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else (256 if res == 64 else 64)
+    only = sys.argv[3] if len(sys.argv) > 3 else None
+    print(f"res={res} B={B}", flush=True)
+    tot = {"fwd": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
+    for div, cin, cout, stride in SHAPES:
+        ho = res // div
+        hi = ho * stride
+        x = torch.randn(B, hi, hi, cin, device=dev).bfloat16()
+        w = (torch.randn(3, 3, cin, cout, device=dev) / (3 * cin ** 0.5)).bfloat16()
+        y = torch.empty(B, ho, ho, cout, device=dev, dtype=torch.bfloat16)
+        dy = torch.randn(B, ho, ho, cout, device=dev).bfloat16()
+        dx = torch.empty_like(x)
+        dw = torch.zeros(3, 3, cin, cout, device=dev)
+        bias = torch.zeros(cout, device=dev)
+        flops = 2.0 * B * ho * ho * 9 * cin * cout
+        runs = {"fwd": lambda: ops.conv3x3_fwd(x, w, bias, out=y, stride=stride),
+                "dgrad": lambda: ops.conv3x3_dgrad(dy, w, dx, stride=stride),
+                "wgrad": lambda: ops.conv3x3_wgrad(x, dy, dw, stride=stride)}
+        line = f"{ho:4d}x{ho:<4d} {cin:4d}->{cout:<4d} s{stride} {flops/1e9:8.1f} GF |"
+        for k, fn in runs.items():
+            if only and k != only:
+                continue
+            ms = timeit(fn)
+            tf = flops / ms / 1e9
+            tot[k][0] += flops
+            tot[k][1] += ms
+            line += f" {k} {ms:7.3f} ms {tf:7.1f} TF/s |"
+        print(line, flush=True)
+        del x, w, y, dy, dx, dw
+    for k, (f, ms) in tot.items():
+        if ms > 0:
+            print(f"TOTAL {k}: {f/1e12:.2f} TFLOP in {ms:.2f} ms = {f/ms/1e9:.1f} TFLOP/s", flush=True)
+    # GroupNorm streaming rate
+    for c, r in ((64, res), (128, res // 2), (512, res // 8)):
+        x = torch.randn(B, r, r, c, device=dev).bfloat16()
+        g, b = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+        st = ops.groupnorm_stats(x, 8)
+        y = torch.empty_like(x)
+        ms1 = timeit(lambda: ops.groupnorm_stats(x, 8))
+        ms2 = timeit(lambda: ops.groupnorm_apply(x, 8, st, g, b, 1e-4, True, out=y))
+        nb = x.numel() * 2
+        print(f"GN {r}x{r}x{c}: stats {nb/ms1/1e6:.0f} GB/s, apply {2*nb/ms2/1e6:.0f} GB/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
