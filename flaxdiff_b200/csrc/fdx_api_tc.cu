@@ -153,6 +153,10 @@ int fdx_conv3x3_wgrad(const fdx_act* x, const fdx_act* dy, float* dw_hwio, int s
   if ((s = check_act(dy, "conv3x3_wgrad dy")) != FDX_OK) return s;
   FDX_REQUIRE(stride == 1 || stride == 2, "conv3x3_wgrad: stride must be 1 or 2");
   FDX_REQUIRE(x->c % 64 == 0 && dy->c % 64 == 0, "conv3x3_wgrad: channels must be multiples of 64");
+  if (stride == 1) {
+    const int r = fdx_wgrad9_launch(x, dy, dw_hwio, (cudaStream_t)stream);
+    if (r != FDX_ERR_UNSUPPORTED) return r;
+  }
   TcLaunch L{};
   L.mode = TC_MNMN;
   fill_act_operand(L.A, x);

@@ -55,34 +55,71 @@ cin3_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w
   }
 }
 
-// ---- conv_in wgrad: dW[t][cs][co] += sum_p x[p+d(t)][cs] * dY[p][co]; db[co] += sum_p dY ----
-__global__ void __launch_bounds__(576)
-cin3_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                  long long dps, int N, int H, int W, int Cout, float* __restrict__ dw,
-                  float* __restrict__ db) {
-  // blockDim = 9 * Cout (Cout == 64); thread = (tap, co)
-  const int t = threadIdx.x / Cout, co = threadIdx.x % Cout;
-  const int ky = t / 3, kx = t % 3;
+// ---- shared weight-gradient kernel of the two 3-channel convolutions ----------------------
+// out[j][c] += sum_p small_j(p) * wide[p][c],  j = (tap t, k in 0..2), c in 0..63, where
+//   small_j(p) = S[p + SGN*d(t)][k]  (zero outside the image).
+//   conv_in :  wide = dY (bf16, 64 ch), S = x_in (bf16, 3 ch), SGN=+1, out = dW[(t*3+k)*64 + c]
+//   conv_out:  wide = x  (bf16, 64 ch), S = dF   (f32, 3 ch),  SGN=-1, out = dW[(t*64+c)*3 + k]
+// Block = 4 pixel lanes x 64 channels; every thread keeps 27 accumulators; wide is read once,
+// fully coalesced; the 27 scalars are warp-broadcast loads that hit L1.
+template <bool SMALL_F32, int SGN>
+__global__ void __launch_bounds__(256)
+rank27_wgrad_kernel(const __nv_bfloat16* __restrict__ wide, long long wps,
+                    const void* __restrict__ small_, int N, int H, int W,
+                    float* __restrict__ dw, float* __restrict__ db) {
+  const int c = threadIdx.x & 63, q = threadIdx.x >> 6;
   const long long npix = (long long)N * H * W;
   const long long per = (npix + gridDim.x - 1) / gridDim.x;
   const long long p0 = blockIdx.x * per, p1 = (p0 + per < npix) ? p0 + per : npix;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
-  for (long long p = p0; p < p1; ++p) {
+  float acc[27];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) acc[j] = 0.f;
+  float accb = 0.f;
+  for (long long p = p0 + q; p < p1; p += 4) {
     const int px = (int)(p % W);
     const int py = (int)((p / W) % H);
-    const float g = __bfloat162float(dy[p * dps + co]);
-    if (t == 4) ab += g;
-    const int iy = py + ky - 1, ix = px + kx - 1;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-    const __nv_bfloat16* xp = x + (p + (long long)(ky - 1) * W + (kx - 1)) * 3;
-    a0 += __bfloat162float(xp[0]) * g;
-    a1 += __bfloat162float(xp[1]) * g;
-    a2 += __bfloat162float(xp[2]) * g;
+    const float v = __bfloat162float(wide[p * wps + c]);
+    if (!SMALL_F32) accb += v;                       // conv_in bias: sum of dY
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int sy = py + SGN * (ky - 1);
+      if (sy < 0 || sy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int sx = px + SGN * (kx - 1);
+        if (sx < 0 || sx >= W) continue;
+        const long long sp = p + (long long)SGN * ((ky - 1) * W + (kx - 1));
+        float s0, s1, s2;
+        if (SMALL_F32) {
+          const float* sm = static_cast<const float*>(small_) + sp * 3;
+          s0 = sm[0]; s1 = sm[1]; s2 = sm[2];
+        } else {
+          const __nv_bfloat16* sm = static_cast<const __nv_bfloat16*>(small_) + sp * 3;
+          s0 = __bfloat162float(sm[0]); s1 = __bfloat162float(sm[1]); s2 = __bfloat162float(sm[2]);
+        }
+        const int t = ky * 3 + kx;
+        acc[t * 3 + 0] += s0 * v; acc[t * 3 + 1] += s1 * v; acc[t * 3 + 2] += s2 * v;
+      }
+    }
+    if (SMALL_F32 && c < 3) accb += static_cast<const float*>(small_)[p * 3 + c];   // conv_out bias
   }
-  atomicAdd(&dw[(t * 3 + 0) * Cout + co], a0);
-  atomicAdd(&dw[(t * 3 + 1) * Cout + co], a1);
-  atomicAdd(&dw[(t * 3 + 2) * Cout + co], a2);
-  if (t == 4 && db) atomicAdd(&db[co], ab);
+  __shared__ float sh[4][28][64];
+#pragma unroll
+  for (int j = 0; j < 27; ++j) sh[q][j][c] = acc[j];
+  sh[q][27][c] = accb;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 28 * 64; i += 256) {
+    const int j = i >> 6, cc = i & 63;
+    const float v = sh[0][j][cc] + sh[1][j][cc] + sh[2][j][cc] + sh[3][j][cc];
+    if (j < 27) {
+      const int t = j / 3, k = j % 3;
+      const int idx = SMALL_F32 ? (t * 64 + cc) * 3 + k : (t * 3 + k) * 64 + cc;
+      atomicAdd(&dw[idx], v);
+    } else if (db) {
+      if (!SMALL_F32) atomicAdd(&db[cc], v);
+      else if (cc < 3) atomicAdd(&db[cc], v);
+    }
+  }
 }
 
 // ---- conv_out forward: x bf16 act [.,Cin], w f32 [9][Cin][3], y f32 [N,H,W,3] -----------
@@ -164,33 +201,6 @@ cout3_dgrad_kernel(const float* __restrict__ dF, const float* __restrict__ w, in
   }
 }
 
-// ---- conv_out wgrad: dW[t][ci][co] += sum_p x[p+d(t)][ci] * dF[p][co]; db[co] += sum dF ---
-__global__ void __launch_bounds__(576)
-cout3_wgrad_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
-                   const float* __restrict__ dF, int N, int H, int W, int Cin,
-                   float* __restrict__ dw, float* __restrict__ db) {
-  // blockDim = 9 * Cin (Cin == 64); thread = (tap, ci)
-  const int t = threadIdx.x / Cin, ci = threadIdx.x % Cin;
-  const int ky = t / 3, kx = t % 3;
-  const long long npix = (long long)N * H * W;
-  const long long per = (npix + gridDim.x - 1) / gridDim.x;
-  const long long p0 = blockIdx.x * per, p1 = (p0 + per < npix) ? p0 + per : npix;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-  for (long long p = p0; p < p1; ++p) {
-    const int px = (int)(p % W);
-    const int py = (int)((p / W) % H);
-    const float g0 = dF[p * 3], g1 = dF[p * 3 + 1], g2 = dF[p * 3 + 2];
-    if (threadIdx.x == 0) { b0 += g0; b1 += g1; b2 += g2; }
-    const int iy = py + ky - 1, ix = px + kx - 1;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-    const float v = __bfloat162float(x[(p + (long long)(ky - 1) * W + (kx - 1)) * xps + ci]);
-    a0 += v * g0; a1 += v * g1; a2 += v * g2;
-  }
-  float* o = dw + ((long long)t * Cin + ci) * 3;
-  atomicAdd(o, a0); atomicAdd(o + 1, a1); atomicAdd(o + 2, a2);
-  if (threadIdx.x == 0 && db) { atomicAdd(db, b0); atomicAdd(db + 1, b1); atomicAdd(db + 2, b2); }
-}
-
 }  // namespace
 
 extern "C" {
@@ -214,9 +224,8 @@ int fdx_conv_in_wgrad(const void* x_bf16, const fdx_act* dy, float* dw_hwio, flo
                       void* stream) {
   FDX_REQUIRE(x_bf16 && dy && dy->ptr && dw_hwio, "conv_in_wgrad: null pointer");
   FDX_REQUIRE(dy->c == 64, "conv_in_wgrad: Cout must be 64 (got %d)", dy->c);
-  cin3_wgrad_kernel<<<148 * 2, 9 * 64, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x_bf16, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, dy->n, dy->h,
-      dy->w, dy->c, dw_hwio, dbias);
+  rank27_wgrad_kernel<false, +1><<<148 * 4, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy->ptr, dy->pix_stride, x_bf16, dy->n, dy->h, dy->w, dw_hwio, dbias);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }
@@ -250,8 +259,8 @@ int fdx_conv_out_wgrad(const fdx_act* x, const float* dF, float* dw_hwio, float*
                        void* stream) {
   FDX_REQUIRE(x && x->ptr && dF && dw_hwio, "conv_out_wgrad: null pointer");
   FDX_REQUIRE(x->c == 64, "conv_out_wgrad: Cin must be 64 (got %d)", x->c);
-  cout3_wgrad_kernel<<<148 * 2, 9 * 64, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x->ptr, x->pix_stride, dF, x->n, x->h, x->w, x->c, dw_hwio, dbias);
+  rank27_wgrad_kernel<true, -1><<<148 * 4, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, dF, x->n, x->h, x->w, dw_hwio, dbias);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

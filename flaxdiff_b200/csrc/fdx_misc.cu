@@ -71,16 +71,19 @@ __global__ void time_embed_bwd_kernel(const float* __restrict__ demb, const floa
   dh1[(long long)b * D + j] = a * gelu_tanh_grad(h1[(long long)b * D + j]);
 }
 
-// dW[k][j] += sum_b in[b][k] * dout[b][j] ; db[j] += sum_b dout[b][j]; grid = D/16 row blocks
+// dW[k][j] += sum_b in[b][k] * dout[b][j] ; db[j] += sum_b dout[b][j]
+// grid = (D/16 row blocks, batch slices); partial sums are combined with f32 atomics
 __global__ void dense_wgrad_small_kernel(const float* __restrict__ in, int apply_gelu,
                                          const float* __restrict__ dout, int B, int D,
                                          float* __restrict__ dW, float* __restrict__ db) {
   const int j = threadIdx.x, k0 = blockIdx.x * 16;
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * per, b1 = min(B, b0 + per);
   float acc[16];
 #pragma unroll
   for (int r = 0; r < 16; ++r) acc[r] = 0.f;
   float accb = 0.f;
-  for (int b = 0; b < B; ++b) {
+  for (int b = b0; b < b1; ++b) {
     const float d = dout[(long long)b * D + j];
     accb += d;
 #pragma unroll
@@ -91,8 +94,8 @@ __global__ void dense_wgrad_small_kernel(const float* __restrict__ in, int apply
     }
   }
 #pragma unroll
-  for (int r = 0; r < 16; ++r) dW[(long long)(k0 + r) * D + j] += acc[r];
-  if (blockIdx.x == 0) db[j] += accb;
+  for (int r = 0; r < 16; ++r) atomicAdd(&dW[(long long)(k0 + r) * D + j], acc[r]);
+  if (blockIdx.x == 0) atomicAdd(&db[j], accb);
 }
 
 // ---- softmax over the last dim; one warp per row; S f32 -> P bf16 ---------------------
@@ -160,9 +163,10 @@ int fdx_time_embed_bwd(const float* demb, const float* four, const float* h1, co
   cudaStream_t st = (cudaStream_t)stream;
   time_embed_bwd_kernel<<<B, D, sizeof(float) * D, st>>>(demb, h1, h2, W2, D, dh1_ws, dh2_ws);
   FDX_LAUNCH_CHECK();
-  dense_wgrad_small_kernel<<<D / 16, D, 0, st>>>(h1, 1, dh2_ws, B, D, dW2, db2);
+  const int bs = B >= 64 ? 16 : (B >= 8 ? 4 : 1);
+  dense_wgrad_small_kernel<<<dim3(D / 16, bs), D, 0, st>>>(h1, 1, dh2_ws, B, D, dW2, db2);
   FDX_LAUNCH_CHECK();
-  dense_wgrad_small_kernel<<<D / 16, D, 0, st>>>(four, 0, dh1_ws, B, D, dW1, db1);
+  dense_wgrad_small_kernel<<<dim3(D / 16, bs), D, 0, st>>>(four, 0, dh1_ws, B, D, dW1, db1);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

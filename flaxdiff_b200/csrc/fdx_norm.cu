@@ -36,6 +36,8 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
 }
 
 // stats[n][g] = (sum, sumsq) accumulated with atomics (buffer zeroed by the caller)
+constexpr int kU = 4;   // pixels in flight per thread (memory-level parallelism)
+
 __global__ void __launch_bounds__(kNT)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps, int HW, int C, int G,
                 float* __restrict__ stats) {
@@ -50,7 +52,22 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps, int HW, int 
     const int g = (cv * 8) / cpg;
     float s = 0.f, q = 0.f;
     const __nv_bfloat16* base = x + (long long)n * HW * xps + cv * 8;
-    for (int p = blockIdx.x * rows + r; p < HW; p += gridDim.x * rows) {
+    const int stride = gridDim.x * rows;
+    int p = blockIdx.x * rows + r;
+    for (; p + (kU - 1) * stride < HW; p += kU * stride) {
+      uint4 u[kU];
+#pragma unroll
+      for (int k = 0; k < kU; ++k)
+        u[k] = *reinterpret_cast<const uint4*>(base + (long long)(p + k * stride) * xps);
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        const float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), c = unpack_bf16x2(u[k].z),
+                     d = unpack_bf16x2(u[k].w);
+        s += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
+        q += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+      }
+    }
+    for (; p < HW; p += stride) {
       float f[8];
       load8(base + (long long)p * xps, f);
 #pragma unroll
@@ -87,7 +104,23 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps, int HW, int 
   }
   const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
   __nv_bfloat16* yb = y + (long long)n * HW * yps + cv * 8;
-  for (int p = blockIdx.x * rows + r; p < HW; p += gridDim.x * rows) {
+  const int stride = gridDim.x * rows;
+  int p = blockIdx.x * rows + r;
+  for (; p + (kU - 1) * stride < HW; p += kU * stride) {
+    float f[kU][8];
+#pragma unroll
+    for (int k = 0; k < kU; ++k) load8(xb + (long long)(p + k * stride) * xps, f[k]);
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z = f[k][j] * a[j] + b[j];
+        f[k][j] = silu ? silu_f(z) : z;
+      }
+      store8(yb + (long long)(p + k * stride) * yps, f[k]);
+    }
+  }
+  for (; p < HW; p += stride) {
     float f[8];
     load8(xb + (long long)p * xps, f);
 #pragma unroll
@@ -130,24 +163,34 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
     float s1 = 0.f, s2 = 0.f;
     const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
     const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
-    for (int p = blockIdx.x * rows + r; p < HW; p += gridDim.x * rows) {
-      float f[8], d[8];
-      load8(xb + (long long)p * xps, f);
-      load8(db_ + (long long)p * dps, d);
+    const int stride = gridDim.x * rows;
+    for (int p0 = blockIdx.x * rows + r; p0 < HW; p0 += 2 * stride) {
+      float f[2][8], d[2][8];
+      const bool two = (p0 + stride) < HW;
+      load8(xb + (long long)p0 * xps, f[0]);
+      load8(db_ + (long long)p0 * dps, d[0]);
+      if (two) {
+        load8(xb + (long long)(p0 + stride) * xps, f[1]);
+        load8(db_ + (long long)(p0 + stride) * dps, d[1]);
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (f[j] - mean) * rstd;
-        float dz = d[j];
-        if (silu) {
-          const float z = xh * ga[j] + be[j];
-          const float sg = 1.f / (1.f + __expf(-z));
-          dz *= sg * (1.f + z * (1.f - sg));
+      for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !two) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (f[k][j] - mean) * rstd;
+          float dz = d[k][j];
+          if (silu) {
+            const float z = xh * ga[j] + be[j];
+            const float sg = sigmoid_fast(z);
+            dz *= sg * (1.f + z * (1.f - sg));
+          }
+          dg[j] += dz * xh;
+          db[j] += dz;
+          const float dxh = dz * ga[j];
+          s1 += dxh;
+          s2 += dxh * xh;
         }
-        dg[j] += dz * xh;
-        db[j] += dz;
-        const float dxh = dz * ga[j];
-        s1 += dxh;
-        s2 += dxh * xh;
       }
     }
     atomicAdd(&sh_red[2 * g], s1);
@@ -167,48 +210,82 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
 }
 
 // backward pass 2: dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat))   (+= if accumulate)
+// Optionally also emits the column sums of dx (what the timestep row-vector / conv bias
+// gradients need) so the caller does not re-read dx: csum_img[n][c] and csum_tot[c].
 __global__ void __launch_bounds__(kNT)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                     const __nv_bfloat16* __restrict__ dy, long long dps, int HW, int C, int G,
                     const float* __restrict__ stats, const float* __restrict__ red,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                    int silu, __nv_bfloat16* __restrict__ dx, long long dxps, int accumulate) {
+                    int silu, __nv_bfloat16* __restrict__ dx, long long dxps, int accumulate,
+                    float* __restrict__ csum_img, float* __restrict__ csum_tot) {
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  if (tid >= rows * vpp) return;
-  const int cv = tid % vpp, r = tid / vpp;
-  const int g = (cv * 8) / cpg;
-  const float cnt = (float)HW * (float)cpg;
-  const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
-  const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
-  const float rstd = rsqrtf(var + eps);
-  const float m1 = red[(long long)n * 2 * G + 2 * g] / cnt;
-  const float m2 = red[(long long)n * 2 * G + 2 * g + 1] / cnt;
-  float ga[8], be[8];
+  extern __shared__ float sh_cs[];   // [C] when column sums are requested
+  const bool want_cs = (csum_img != nullptr) || (csum_tot != nullptr);
+  if (want_cs) {
+    for (int i = tid; i < C; i += kNT) sh_cs[i] = 0.f;
+    __syncthreads();
+  }
+  if (tid < rows * vpp) {
+    const int cv = tid % vpp, r = tid / vpp;
+    const int g = (cv * 8) / cpg;
+    const float cnt = (float)HW * (float)cpg;
+    const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
+    const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+    const float rstd = rsqrtf(var + eps);
+    const float m1 = red[(long long)n * 2 * G + 2 * g] / cnt;
+    const float m2 = red[(long long)n * 2 * G + 2 * g + 1] / cnt;
+    float ga[8], be[8], cs[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { ga[j] = gamma[cv * 8 + j]; be[j] = beta[cv * 8 + j]; }
-  const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
-  const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
-  __nv_bfloat16* ob = dx + (long long)n * HW * dxps + cv * 8;
-  for (int p = blockIdx.x * rows + r; p < HW; p += gridDim.x * rows) {
-    float f[8], d[8], o[8];
-    load8(xb + (long long)p * xps, f);
-    load8(db_ + (long long)p * dps, d);
-    if (accumulate) load8(ob + (long long)p * dxps, o);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (f[j] - mean) * rstd;
-      float dz = d[j];
-      if (silu) {
-        const float z = xh * ga[j] + be[j];
-        const float sg = 1.f / (1.f + __expf(-z));
-        dz *= sg * (1.f + z * (1.f - sg));
+    for (int j = 0; j < 8; ++j) { ga[j] = gamma[cv * 8 + j]; be[j] = beta[cv * 8 + j]; cs[j] = 0.f; }
+    const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
+    const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
+    __nv_bfloat16* ob = dx + (long long)n * HW * dxps + cv * 8;
+    const int stride = gridDim.x * rows;
+    for (int p0 = blockIdx.x * rows + r; p0 < HW; p0 += 2 * stride) {
+      float f[2][8], d[2][8], o[2][8];
+      const bool two = (p0 + stride) < HW;
+      load8(xb + (long long)p0 * xps, f[0]);
+      load8(db_ + (long long)p0 * dps, d[0]);
+      if (accumulate) load8(ob + (long long)p0 * dxps, o[0]);
+      if (two) {
+        load8(xb + (long long)(p0 + stride) * xps, f[1]);
+        load8(db_ + (long long)(p0 + stride) * dps, d[1]);
+        if (accumulate) load8(ob + (long long)(p0 + stride) * dxps, o[1]);
       }
-      const float v = rstd * (dz * ga[j] - m1 - xh * m2);
-      o[j] = accumulate ? o[j] + v : v;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !two) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (f[k][j] - mean) * rstd;
+          float dz = d[k][j];
+          if (silu) {
+            const float z = xh * ga[j] + be[j];
+            const float sg = sigmoid_fast(z);
+            dz *= sg * (1.f + z * (1.f - sg));
+          }
+          const float v = rstd * (dz * ga[j] - m1 - xh * m2);
+          cs[j] += v;
+          o[k][j] = accumulate ? o[k][j] + v : v;
+        }
+        store8(ob + (long long)(p0 + k * stride) * dxps, o[k]);
+      }
     }
-    store8(ob + (long long)p * dxps, o);
+    if (want_cs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sh_cs[cv * 8 + j], cs[j]);
+    }
+  }
+  if (want_cs) {
+    __syncthreads();
+    for (int c = tid; c < C; c += kNT) {
+      const float v = sh_cs[c];
+      if (csum_img) atomicAdd(&csum_img[(long long)n * C + c], v);
+      if (csum_tot) atomicAdd(&csum_tot[c], v);
+    }
   }
 }
 
@@ -314,14 +391,15 @@ int gn_check(const fdx_act* x, int groups, const char* what) {
   return FDX_OK;
 }
 
-dim3 gn_grid(const fdx_act* x) {
+dim3 gn_grid(const fdx_act* x, int unroll) {
   const int HW = x->h * x->w;
   const int rows = kNT / (x->c / 8);
-  int bx = (HW + rows - 1) / rows;
-  // enough blocks to fill the machine, but keep >= ~8 pixels per thread row
-  int target = (4 * 148 + x->n - 1) / x->n;
+  int bx = (HW + rows * unroll - 1) / (rows * unroll);
+  // ~16 resident blocks per SM keeps enough 16-byte loads in flight to saturate HBM
+  int target = (16 * 148 + x->n - 1) / x->n;
   if (target < 1) target = 1;
   if (bx > target) bx = target;
+  if (bx < 1) bx = 1;
   return dim3(bx, x->n);
 }
 
@@ -334,7 +412,7 @@ int fdx_groupnorm_stats(const fdx_act* x, int groups, float* stats, void* stream
   if (s != FDX_OK) return s;
   cudaStream_t st = (cudaStream_t)stream;
   FDX_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * x->n, st));
-  gn_stats_kernel<<<gn_grid(x), kNT, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pix_stride,
+  gn_stats_kernel<<<gn_grid(x, kU), kNT, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pix_stride,
                                               x->h * x->w, x->c, groups, stats);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
@@ -346,7 +424,7 @@ int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const 
   if (s != FDX_OK) return s;
   FDX_REQUIRE(y && y->ptr && y->n == x->n && y->h == x->h && y->w == x->w && y->c == x->c,
               "groupnorm_apply: output shape mismatch");
-  gn_apply_kernel<<<gn_grid(x), kNT, 0, (cudaStream_t)stream>>>(
+  gn_apply_kernel<<<gn_grid(x, kU), kNT, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x->ptr, x->pix_stride, x->h * x->w, x->c, groups, stats, gamma, beta,
       eps, silu, (__nv_bfloat16*)y->ptr, y->pix_stride);
   FDX_LAUNCH_CHECK();
@@ -356,7 +434,7 @@ int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const 
 int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
                       const float* gamma, const float* beta, float eps, int silu, float* red,
                       float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
-                      void* stream) {
+                      float* csum_img, float* csum_tot, void* stream) {
   int s = gn_check(x, groups, "groupnorm_bwd");
   if (s != FDX_OK) return s;
   FDX_REQUIRE(dy && dy->ptr && dx && dx->ptr, "groupnorm_bwd: null tensor");
@@ -366,14 +444,17 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
   cudaStream_t st = (cudaStream_t)stream;
   FDX_CUDA(cudaMemsetAsync(red, 0, sizeof(float) * 2 * groups * x->n, st));
   const size_t shm = sizeof(float) * (2 * groups + 2 * x->c);
-  gn_bwd_stats_kernel<<<gn_grid(x), kNT, shm, st>>>(
+  gn_bwd_stats_kernel<<<gn_grid(x, 2), kNT, shm, st>>>(
       (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride,
       x->h * x->w, x->c, groups, stats, gamma, beta, eps, silu, red, dgamma, dbeta);
   FDX_LAUNCH_CHECK();
-  gn_bwd_apply_kernel<<<gn_grid(x), kNT, 0, st>>>(
+  if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * x->n * x->c, st));
+  if (csum_tot) FDX_CUDA(cudaMemsetAsync(csum_tot, 0, sizeof(float) * x->c, st));
+  const size_t shm2 = (csum_img || csum_tot) ? sizeof(float) * x->c : 0;
+  gn_bwd_apply_kernel<<<gn_grid(x, 2), kNT, shm2, st>>>(
       (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride,
       x->h * x->w, x->c, groups, stats, red, gamma, beta, eps, silu, (__nv_bfloat16*)dx->ptr,
-      dx->pix_stride, accumulate);
+      dx->pix_stride, accumulate, csum_img, csum_tot);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

@@ -336,7 +336,22 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long xps, int HW, int C,
     const int cv = tid % vpp, r = tid / vpp;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const __nv_bfloat16* base = x + (long long)n * HW * xps + cv * 8;
-    for (int p = blockIdx.x * rows + r; p < HW; p += gridDim.x * rows) {
+    const int stride = gridDim.x * rows;
+    int p = blockIdx.x * rows + r;
+    for (; p + 3 * stride < HW; p += 4 * stride) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        u[k] = *reinterpret_cast<const uint4*>(base + (long long)(p + k * stride) * xps);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), c = unpack_bf16x2(u[k].z),
+               d = unpack_bf16x2(u[k].w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      }
+    }
+    for (; p < HW; p += stride) {
       const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)p * xps);
       float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
              d = unpack_bf16x2(u.w);
@@ -485,8 +500,8 @@ int fdx_colsum(const fdx_act* x, float* out, int per_image, void* stream) {
   FDX_REQUIRE(x->c % 8 == 0 && x->c / 8 <= 256, "colsum: bad channel count %d", x->c);
   const int HW = x->h * x->w;
   const int rows = 256 / (x->c / 8);
-  int bx = (HW + rows - 1) / rows;
-  int target = (4 * 148 + x->n - 1) / x->n;
+  int bx = (HW + 4 * rows - 1) / (4 * rows);
+  int target = (16 * 148 + x->n - 1) / x->n;
   if (bx > target) bx = target;
   if (bx < 1) bx = 1;
   cudaStream_t st = (cudaStream_t)stream;

@@ -26,7 +26,7 @@ constexpr int kABytes = 128 * kBK * 2;  // 16 KB per stage for A in every mode
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = (BN == 64) ? 8 : (BN == 128) ? 6 : 4;
+  static constexpr int kStages = (BN == 64) ? 8 : (BN == 128) ? 6 : 4;   // BN = 192, 256: 4
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -48,6 +48,8 @@ struct TcDev {
   int Ncols, nblks;      // column blocks of BN
   int b_batched;
   int mn_batched;        // TC_MNMN: reduce over x blocks only, (y, n) blocks are batch
+  int tpp;               // TC_MNMN: taps per tile (2 when M <= 64: two taps share one M=128 MMA)
+  int ntp;               // TC_MNMN: number of tap groups = ceil(ntaps / tpp)
   int splits;
   int ntiles;
   // epilogue
@@ -66,14 +68,16 @@ struct MnTile {
   int bz, sp, nt, mb, t, pb0, pb1;
 };
 __device__ __forceinline__ MnTile decode_mn(const TcDev& p, int tile) {
+  // fastest -> slowest: tap group, column block, row block, batch block, K split.  CTAs that run
+  // concurrently therefore work on the same pixel range and share A / B boxes in L2.
   MnTile m;
   int r = tile;
   const int nbz = p.mn_batched ? p.nyb * p.nnb : 1;
-  m.bz = r % nbz; r /= nbz;
-  m.sp = r % p.splits; r /= p.splits;
+  m.t = r % p.ntp;     r /= p.ntp;
   m.nt = r % p.nblks;  r /= p.nblks;
   m.mb = r % p.mblks;  r /= p.mblks;
-  m.t = r;
+  m.bz = r % nbz;      r /= nbz;
+  m.sp = r;
   const long long kblocks = p.mn_batched ? p.nxb : (long long)p.nxb * p.nyb * p.nnb;
   m.pb0 = (int)((kblocks * m.sp) / p.splits);
   m.pb1 = (int)((kblocks * (m.sp + 1)) / p.splits);
@@ -178,11 +182,17 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + kABytes;
             mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-            const int ax = xb * p.TW * p.es + p.tap_dx[t], ay = yb * p.TH * p.es + p.tap_dy[t];
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              tma_load_4d(sa + j * (kBK * 128), &mapA, &full[stage], mb * 128 + j * 64, ax, ay,
-                          nb * p.TN);
+            for (int j = 0; j < 2; ++j) {
+              // tpp == 1: the two 64-channel halves of row block mb for tap t
+              // tpp == 2: channels [0,64) of taps 2t and 2t+1 (a missing tap reads out of range = 0)
+              const int tap = (p.tpp == 2) ? (2 * t + j) : t;
+              const bool live = tap < p.ntaps;
+              const int tt = live ? tap : 0;
+              const int ch = (p.tpp == 2) ? (live ? 0 : (int)p.M + 64) : (mb * 128 + j * 64);
+              tma_load_4d(sa + j * (kBK * 128), &mapA, &full[stage], ch,
+                          xb * p.TW * p.es + p.tap_dx[tt], yb * p.TH * p.es + p.tap_dy[tt], nb * p.TN);
+            }
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
               tma_load_4d(sb + j * (kBK * 128), &mapB, &full[stage], nt * BN + j * 64, xb * p.TW,
@@ -263,9 +273,11 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       } else {
         const MnTile mt_ = decode_mn(p, tile);
         nt = mt_.nt;
-        const int m = mt_.mb * 128 + row;
-        valid = m < p.M;
-        obase = (long long)p.tap_b[mt_.t] * p.os_tap + (long long)m * p.os_m;
+        int m, tap;
+        if (p.tpp == 2) { m = row & 63; tap = 2 * mt_.t + (row >> 6); }
+        else            { m = mt_.mb * 128 + row; tap = mt_.t; }
+        valid = (m < p.M) && (tap < p.ntaps);
+        obase = (long long)p.tap_b[valid ? tap : 0] * p.os_tap + (long long)m * p.os_m;
         if (p.mn_batched)
           obase += (long long)(mt_.bz % p.nyb) * p.os_y + (long long)(mt_.bz / p.nyb) * p.os_n;
         has_acc = (mt_.pb1 - mt_.pb0) > 0;
@@ -366,6 +378,7 @@ int launch_mode(int BN, const CUtensorMap& mA, const CUtensorMap& mB, const TcDe
   switch (BN) {
     case 64: return launch_cfg<64, MODE>(mA, mB, d, stream);
     case 128: return launch_cfg<128, MODE>(mA, mB, d, stream);
+    case 192: return launch_cfg<192, MODE>(mA, mB, d, stream);
     case 256: return launch_cfg<256, MODE>(mA, mB, d, stream);
   }
   fdx_set_error("tc: unsupported BN %d", BN);
@@ -398,8 +411,18 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
   d.rs_x = L.rs_x; d.rs_y = L.rs_y; d.rs_n = L.rs_n;
 
   // ---- column tile --------------------------------------------------------
-  int BN = (L.Ncols % 256 == 0) ? 256 : (L.Ncols % 128 == 0) ? 128 : 64;
-  // keep enough tiles in flight for 148 SMs: shrink BN if the grid would be tiny
+  // cost model per row tile: ntiles * (BN + 64)  (MMA columns incl. padding + A re-read per tile)
+  int BN = 64;
+  {
+    long long best = -1;
+    const int cands[4] = {256, 192, 128, 64};
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cands[i];
+      const long long nt = (L.Ncols + bn - 1) / bn;
+      const long long cost = nt * (bn + 64);
+      if (best < 0 || cost < best) { best = cost; BN = bn; }
+    }
+  }
   const int rows_per_tile = (L.mode == TC_MNMN) ? 64 : 128;
   // ---- pixel box ----------------------------------------------------------
   int TW, TH, TN;
@@ -423,26 +446,42 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
   const long long pix_blocks = (long long)d.nxb * d.nyb * d.nnb;
 
   if (L.mode != TC_MNMN) {
-    while (BN > 64 && pix_blocks * ((L.Ncols + BN - 1) / BN) < 2LL * fdx_num_sms()) BN /= 2;
+    while (BN > 64 && pix_blocks * ((L.Ncols + BN - 1) / BN) < 2LL * fdx_num_sms())
+      BN = (BN == 192) ? 64 : BN / 2;
     d.nblks = (L.Ncols + BN - 1) / BN;
     d.kchunks = (L.K + kBK - 1) / kBK;
     d.ntiles = (int)(pix_blocks * d.nblks);
     d.splits = 1;
     d.mblks = 1;
+    d.tpp = 1;
+    d.ntp = L.ntaps;
     FDX_REQUIRE(!L.res || !L.out_atomic, "tc: residual with atomic output unsupported");
   } else {
-    if (BN > 128) BN = 128;   // 2 A blocks + BN/64 B blocks of 8 KB per stage
     d.nblks = (L.Ncols + BN - 1) / BN;
+    d.tpp = (L.M <= 64 && L.ntaps > 1) ? 2 : 1;
+    d.ntp = (L.ntaps + d.tpp - 1) / d.tpp;
     d.mblks = (L.M + 127) / 128;
     d.kchunks = 0;
-    long long base_tiles = (long long)L.ntaps * d.mblks * d.nblks;
+    long long base_tiles = (long long)d.ntp * d.mblks * d.nblks;
     const long long kblocks = L.mn_batched ? d.nxb : pix_blocks;
     const long long nbz = L.mn_batched ? (long long)d.nyb * d.nnb : 1;
     int splits = L.splits;
     if (splits <= 0) {
+      // wave-aware split-K: pick the split count whose tile total fills w waves of the machine
+      // best (w = 1..4); more waves only when they raise the fill by > 3 %.
       const int sms = fdx_num_sms();
-      splits = (int)((2LL * sms + base_tiles * nbz - 1) / (base_tiles * nbz));
-      if (splits < 1) splits = 1;
+      const long long bt = base_tiles * nbz;
+      double best_eff = -1.0;
+      splits = 1;
+      for (int w = 1; w <= 4; ++w) {
+        long long sp = ((long long)sms * w) / bt;
+        if (sp < 1) sp = 1;
+        if (sp > kblocks) sp = kblocks;
+        const long long tiles = bt * sp;
+        const long long waves = (tiles + sms - 1) / sms;
+        const double eff = (double)tiles / (double)(waves * sms);
+        if (eff > best_eff + 0.03) { best_eff = eff; splits = (int)sp; }
+      }
     }
     if (splits > kblocks) splits = (int)kblocks;
     FDX_REQUIRE(splits == 1 || L.out_atomic, "tc: split-K needs atomic output");

@@ -9,6 +9,7 @@
 // wgrad, 1x1 conv, dense layer and the attention contractions.
 #pragma once
 #include "fdx_common.cuh"
+#include "../../include/fdx.h"
 
 struct TcOperand {
   const void* ptr;        // bf16
@@ -53,3 +54,6 @@ struct TcLaunch {
 };
 
 int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream);
+
+// All-nine-taps weight-gradient kernel (fdx_wgrad9.cu); FDX_ERR_UNSUPPORTED = shape not covered.
+int fdx_wgrad9_launch(const fdx_act* x, const fdx_act* dy, float* dw, cudaStream_t stream);

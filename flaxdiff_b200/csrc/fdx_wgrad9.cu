@@ -1,0 +1,233 @@
+// fdx_wgrad9.cu -- 3x3 convolution weight gradient with all nine taps in one CTA.
+//
+//   dW[ky][kx][ci][co] = sum_{n,y,x} X[n, y+ky-1, x+kx-1, ci] * dY[n, y, x, co]
+// (the weight half of jax.value_and_grad through flax nn.Conv, flaxdiff/models/common.py:166-172 via
+//  trainer/general_diffusion_trainer.py:321-322).
+//
+// The generic split-K engine (fdx_tc.cu, TC_MNMN) re-reads X and dY from L2 once per (tap, row block,
+// column block): 43-85 FLOP per L2 byte, which is L2-bandwidth-bound on B200 (measured 200-750 TF/s).
+// Here one CTA owns a 64(ci) x 64(co) block of ALL nine taps for its slice of the pixels:
+//   * per 64-pixel block (16x4 or 8x8 patch) TMA brings ONE dY box and THREE X boxes - one per kx
+//     shift, each (TH+2) rows tall - so the three ky shifts of a box are plain row offsets of
+//     ky*TW*128 B: multiples of 1024 B, i.e. swizzle-aligned views of the same shared memory;
+//   * the nine taps are five tcgen05.mma groups of M=128 (two taps x 64 channels: the MN-major
+//     descriptor's leading-dimension offset jumps from one tap's view to the next), N=64, into
+//     five TMEM accumulators (320 columns);
+//   * X traffic drops from 9 to 3*(TH+2)/TH boxes per block: 107 FLOP per L2 byte.
+// Tiles = (ci block, co block, pixel split); split-K partial sums are combined with f32 atomics.
+#include "fdx_common.cuh"
+#include "../../include/fdx.h"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kStages = 4;
+
+struct W9Dev {
+  int TW, TH;              // pixel patch (TW*TH == 64)
+  int nxb, nyb, nimg;
+  int Cin, Cout, cib, cob;
+  int splits, ntiles;
+  float* dw;               // [9][Cin][Cout] f32, accumulated
+};
+
+// tap order sorted by shared-memory address of its view: (kx, ky) lexicographic
+__device__ __forceinline__ int tap_of_slot(int slot) {   // slot 0..8 -> tap index ky*3+kx
+  const int kx = slot / 3, ky = slot % 3;
+  return ky * 3 + kx;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+fdx_wgrad9_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+                  const W9Dev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int xbuf_bytes = (p.TH + 2) * p.TW * 128;      // one kx box (rows of 64 bf16 channels)
+  const int ybuf_bytes = 64 * 128;
+  const int stage_bytes = 3 * xbuf_bytes + ybuf_bytes; // multiple of 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = bars + 2 * kStages + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapY);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long kblocks = (long long)p.nxb * p.nyb * p.nimg;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int r = tile;
+        const int cb = r % p.cib; r /= p.cib;
+        const int ob = r % p.cob; r /= p.cob;
+        const int sp = r;
+        const int pb0 = (int)((kblocks * sp) / p.splits), pb1 = (int)((kblocks * (sp + 1)) / p.splits);
+        for (int pb = pb0; pb < pb1; ++pb) {
+          const int xb = pb % p.nxb, yb = (pb / p.nxb) % p.nyb, nb = pb / (p.nxb * p.nyb);
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sx = smem + stage * stage_bytes;
+          uint8_t* sy = sx + 3 * xbuf_bytes;
+          mbar_arrive_expect_tx(&full[stage], stage_bytes);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            tma_load_4d(sx + kx * xbuf_bytes, &mapX, &full[stage], cb * 64, xb * p.TW + kx - 1,
+                        yb * p.TH - 1, nb);
+          tma_load_4d(sy, &mapY, &full[stage], ob * 64, xb * p.TW, yb * p.TH, nb);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      int stage = 0; uint32_t phase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int sp = tile / (p.cib * p.cob);
+        const int nk = (int)((kblocks * (sp + 1)) / p.splits) - (int)((kblocks * sp) / p.splits);
+        mbar_wait(tempty, tphase ^ 1);
+        tc_fence_after();
+        for (int i = 0; i < nk; ++i) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sx = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sy = sx + 3 * xbuf_bytes;
+#pragma unroll
+          for (int g = 0; g < 5; ++g) {
+            // slots 2g, 2g+1 (slot 9 does not exist: its rows are computed on slot 8's view and dropped)
+            const int s0 = 2 * g, s1 = (2 * g + 1 < 9) ? 2 * g + 1 : 2 * g;
+            const uint32_t v0 = sx + (s0 / 3) * xbuf_bytes + (s0 % 3) * p.TW * 128;
+            const uint32_t v1 = sx + (s1 / 3) * xbuf_bytes + (s1 % 3) * p.TW * 128;
+            const uint32_t lbo = (v1 > v0) ? (v1 - v0) : 1024;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = umma_desc_sw128(v0 + k * 2048, lbo, 1024);
+              const uint64_t db = umma_desc_sw128(sy + k * 2048, 8192, 1024);
+              umma_f16(tmem_base + g * 64, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull);
+        tphase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int r = tile;
+      const int cb = r % p.cib; r /= p.cib;
+      const int ob = r % p.cob;
+      const int ci = cb * 64 + (row & 63);
+      mbar_wait(tfull, tphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < 5; ++g) {
+        const int slot = 2 * g + (row >> 6);
+        const bool valid = (slot < 9) && (ci < p.Cin);
+        const int tap = valid ? tap_of_slot(slot) : 0;
+        float* out = p.dw + ((long long)tap * p.Cin + ci) * p.Cout + ob * 64;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + c0), v);
+          tmem_ld_wait();
+          if (valid && ob * 64 + c0 < p.Cout) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(out + c0 + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      tphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace
+
+// Returns FDX_ERR_UNSUPPORTED (without setting an error) when the shape does not fit this kernel;
+// the caller then uses the generic engine.
+int fdx_wgrad9_launch(const fdx_act* x, const fdx_act* dy, float* dw, cudaStream_t stream) {
+  const int W = dy->w, H = dy->h;
+  if (W < 8 || (W & (W - 1)) != 0 || (H & (H - 1)) != 0) return FDX_ERR_UNSUPPORTED;
+  if (x->w != W || x->h != H) return FDX_ERR_UNSUPPORTED;
+  W9Dev d{};
+  d.TW = W >= 16 ? 16 : 8;
+  d.TH = 64 / d.TW;
+  if (H < d.TH) return FDX_ERR_UNSUPPORTED;
+  d.nxb = W / d.TW; d.nyb = H / d.TH; d.nimg = dy->n;
+  d.Cin = x->c; d.Cout = dy->c;
+  d.cib = (x->c + 63) / 64; d.cob = (dy->c + 63) / 64;
+  d.dw = dw;
+  const long long kblocks = (long long)d.nxb * d.nyb * d.nimg;
+  const long long bt = (long long)d.cib * d.cob;
+  const int sms = fdx_num_sms();
+  if (sms <= 0) return FDX_ERR_NO_DEVICE;
+  double best = -1.0; int splits = 1;
+  for (int w = 1; w <= 4; ++w) {
+    long long sp = ((long long)sms * w) / bt;
+    if (sp < 1) sp = 1;
+    if (sp > kblocks) sp = kblocks;
+    const long long tiles = bt * sp, waves = (tiles + sms - 1) / sms;
+    const double eff = (double)tiles / (double)(waves * sms);
+    if (eff > best + 0.03) { best = eff; splits = (int)sp; }
+  }
+  d.splits = splits;
+  d.ntiles = (int)(bt * splits);
+
+  CUtensorMap mX, mY;
+  {
+    uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+    uint64_t str[3] = {(uint64_t)x->pix_stride * 2, (uint64_t)x->pix_stride * x->w * 2,
+                       (uint64_t)x->pix_stride * x->w * x->h * 2};
+    uint32_t box[4] = {64, (uint32_t)d.TW, (uint32_t)(d.TH + 2), 1};
+    uint32_t est[4] = {1, 1, 1, 1};
+    int s = fdx_make_tmap_bf16(&mX, x->ptr, 4, dims, str, box, est, 1);
+    if (s != FDX_OK) return s;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)dy->c, (uint64_t)dy->w, (uint64_t)dy->h, (uint64_t)dy->n};
+    uint64_t str[3] = {(uint64_t)dy->pix_stride * 2, (uint64_t)dy->pix_stride * dy->w * 2,
+                       (uint64_t)dy->pix_stride * dy->w * dy->h * 2};
+    uint32_t box[4] = {64, (uint32_t)d.TW, (uint32_t)d.TH, 1};
+    uint32_t est[4] = {1, 1, 1, 1};
+    int s = fdx_make_tmap_bf16(&mY, dy->ptr, 4, dims, str, box, est, 1);
+    if (s != FDX_OK) return s;
+  }
+  const int stage_bytes = 3 * (d.TH + 2) * d.TW * 128 + 64 * 128;
+  const int smem_bytes = kStages * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FDX_CUDA(cudaFuncSetAttribute(fdx_wgrad9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kStages * (3 * 6 * 16 * 128 + 64 * 128) + 1024 + 256));
+    attr_set = true;
+  }
+  int grid = sms < d.ntiles ? sms : d.ntiles;
+  fdx_wgrad9_kernel<<<grid, kThreads, smem_bytes, stream>>>(mX, mY, d);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}

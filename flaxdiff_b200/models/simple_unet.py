@@ -515,12 +515,13 @@ class Unet:
         ops.conv3x3_dgrad(dout, W16[f"{name}/conv2/conv/kernel"], da2)
         # norm2 + silu
         dh = torch.empty_like(hmid)
+        # the same pass also emits the per-image / total column sums of dh: the timestep
+        # row-vector gradient and the conv1 (= temb_projection) bias gradient
+        drow = torch.empty((Bn, cout), dtype=F32, device=x.device)
         ops.groupnorm_bwd(hmid, da2, G, st2, W[f"{name}/{self._n2}/scale"], W[f"{name}/{self._n2}/bias"], RES_EPS,
-                          True, Gd[f"{name}/{self._n2}/scale"], Gd[f"{name}/{self._n2}/bias"], dh, False)
+                          True, Gd[f"{name}/{self._n2}/scale"], Gd[f"{name}/{self._n2}/bias"], dh, False,
+                          csum_img=drow, csum_tot=Gd[f"{name}/conv1/conv/bias"])
         del da2
-        # timestep row-vector and conv1 bias
-        drow = ops.colsum(dh, True)                                   # [B, cout] f32
-        ops.colsum(dh, False, out=Gd[f"{name}/conv1/conv/bias"])
         Gd[f"{name}/temb_projection/bias"].copy_(Gd[f"{name}/conv1/conv/bias"])
         drow16 = ops.cast_f32_bf16(drow)
         ops.gemm(GEMM_MNMN, emb16, drow16, Gd[f"{name}/temb_projection/kernel"], E, cout, Bn, E, cout, cout,

@@ -27,7 +27,7 @@ extern "C" {
 #define FDX_ERR_CUDA (-3)
 #define FDX_ERR_NO_DEVICE (-4)
 
-typedef struct {
+typedef struct fdx_act {
   void* ptr;            /* device pointer to element (n=0,y=0,x=0,c=0) */
   int n, h, w, c;       /* logical dims */
   long long pix_stride; /* elements between consecutive pixels (>= c, multiple of 8) */
@@ -81,11 +81,13 @@ int fdx_groupnorm_stats(const fdx_act* x, int groups, float* stats, void* stream
 /* y = silu?((x-mean)*rstd*gamma+beta) (models/common.py:286-288,310-312; simple_unet.py:209-210). */
 int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const float* gamma,
                         const float* beta, float eps, int silu, const fdx_act* y, void* stream);
-/* Backward of the pair above. red: [n][g][2] f32 scratch; dgamma/dbeta ACCUMULATED. */
+/* Backward of the pair above. red: [n][g][2] f32 scratch; dgamma/dbeta ACCUMULATED.
+ * csum_img [n][c] / csum_tot [c] (either may be NULL): column sums over pixels of the dx this call
+ * produces, written (not accumulated) - the timestep row-vector and conv-bias gradients. */
 int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
                       const float* gamma, const float* beta, float eps, int silu, float* red,
                       float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
-                      void* stream);
+                      float* csum_img, float* csum_tot, void* stream);
 /* nn.RMSNorm(eps) over channels (models/attention.py:325-326). C in {256,512,768,1024}. */
 int fdx_rmsnorm_fwd(const fdx_act* x, const float* scale, float eps, const fdx_act* y,
                     void* stream);

@@ -41,8 +41,10 @@ def test_groupnorm_fwd_bwd(shape, silu):
     yr.backward(dy.float().cpu())
     dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
     dx = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
-    ops.groupnorm_bwd(x, dy, 8, st, gamma, beta, 1e-4, silu, dg, db, dx)
+    ci, ct = torch.empty(B, C, device=dev), torch.empty(C, device=dev)
+    ops.groupnorm_bwd(x, dy, 8, st, gamma, beta, 1e-4, silu, dg, db, dx, csum_img=ci, csum_tot=ct)
     assert rel(dx, xr.grad) < 1e-2
+    assert rel(ci, xr.grad.sum((1, 2))) < 2e-2 and rel(ct, xr.grad.sum((0, 1, 2))) < 2e-2
     assert rel(dg, gr.grad) < 5e-3 and rel(db, br.grad) < 5e-3
     base = torch.randn_like(dx.float()).bfloat16()
     dx2 = base.clone()

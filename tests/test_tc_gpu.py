@@ -33,6 +33,9 @@ CASES = [
     ("conv_wgrad", lambda: T.t_conv_wgrad(2, 16, 16, 64, 64), F32_TOL),
     ("conv_wgrad_wide", lambda: T.t_conv_wgrad(4, 32, 32, 192, 128), F32_TOL),
     ("conv_wgrad_stride2", lambda: T.t_conv_wgrad(2, 32, 32, 64, 128, stride=2), F32_TOL),
+    ("conv_wgrad_8x8_tile", lambda: T.t_conv_wgrad(6, 8, 8, 256, 128), F32_TOL),
+    ("conv_wgrad_many_splits", lambda: T.t_conv_wgrad(16, 64, 64, 64, 64), F32_TOL),
+    ("conv_wgrad_4x4_generic", lambda: T.t_conv_wgrad(8, 4, 4, 128, 64), F32_TOL),
     ("attn_qk_d64", lambda: T.t_attn_qk(2, 256, 8, 64), BF16_TOL),
     ("attn_qk_d32", lambda: T.t_attn_qk(2, 128, 8, 32), BF16_TOL),
     ("attn_pv_d64", lambda: T.t_attn_pv(2, 256, 8, 64), BF16_TOL),
