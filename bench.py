@@ -176,7 +176,7 @@ def log(msg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fdx", choices=["fdx", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))

@@ -132,7 +132,18 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps, int HW, int 
   }
 }
 
-// backward pass 1: red[n][g] = (sum dxhat, sum dxhat*xhat); dgamma/dbeta accumulated (atomics)
+// ---- GroupNorm(+SiLU) backward ---------------------------------------------------------------
+// With a_c = rstd*gamma_c, b_c = beta_c - mean*a_c:  z = a_c*x + b_c,  dz = dy * silu'(z).
+// Pass 1 needs only two per-(image, channel) sums, S0 = sum dz and S1 = sum dz*x, because
+//   dbeta_c  = sum_n S0                       dgamma_c = sum_n rstd*(S1 - mean*S0)
+//   red[n][g] = ( sum_{c in g} gamma_c*S0 ,   sum_{c in g} gamma_c*rstd*(S1 - mean*S0) )
+// and pass 2 is  dx = dz*a_c - x*c2 + c3  with per-group c2 = rstd^2*m2, c3 = mean*c2 - rstd*m1.
+// Both passes are instruction-issue sensitive (two MUFU per element), hence the reduced algebra.
+__device__ __forceinline__ float silu_grad_times(float dy, float z) {
+  const float sg = sigmoid_fast(z);
+  return dy * sg * (1.f + z * (1.f - sg));
+}
+
 __global__ void __launch_bounds__(kNT)
 gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                     const __nv_bfloat16* __restrict__ dy, long long dps, int HW, int C, int G,
@@ -144,23 +155,24 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
   const int tid = threadIdx.x;
   extern __shared__ float shm[];   // [2*G] + [2*C]
   float* sh_red = shm;
-  float* sh_dg = shm + 2 * G;
-  float* sh_db = sh_dg + C;
+  float* sh_s0 = shm + 2 * G;
+  float* sh_s1 = sh_s0 + C;
   for (int i = tid; i < 2 * G + 2 * C; i += kNT) shm[i] = 0.f;
   __syncthreads();
+  const float cnt = (float)HW * (float)cpg;
   if (tid < rows * vpp) {
     const int cv = tid % vpp, r = tid / vpp;
     const int g = (cv * 8) / cpg;
-    const float cnt = (float)HW * (float)cpg;
     const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
     const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
     const float rstd = rsqrtf(var + eps);
-    float ga[8], be[8], dg[8], db[8];
+    float a[8], b[8], s0[8], s1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      ga[j] = gamma[cv * 8 + j]; be[j] = beta[cv * 8 + j]; dg[j] = 0.f; db[j] = 0.f;
+      a[j] = rstd * gamma[cv * 8 + j];
+      b[j] = beta[cv * 8 + j] - mean * a[j];
+      s0[j] = 0.f; s1[j] = 0.f;
     }
-    float s1 = 0.f, s2 = 0.f;
     const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
     const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
     const int stride = gridDim.x * rows;
@@ -178,40 +190,37 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
         if (k == 1 && !two) break;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (f[k][j] - mean) * rstd;
-          float dz = d[k][j];
-          if (silu) {
-            const float z = xh * ga[j] + be[j];
-            const float sg = sigmoid_fast(z);
-            dz *= sg * (1.f + z * (1.f - sg));
-          }
-          dg[j] += dz * xh;
-          db[j] += dz;
-          const float dxh = dz * ga[j];
-          s1 += dxh;
-          s2 += dxh * xh;
+          const float dz = silu ? silu_grad_times(d[k][j], f[k][j] * a[j] + b[j]) : d[k][j];
+          s0[j] += dz;
+          s1[j] += dz * f[k][j];
         }
       }
     }
-    atomicAdd(&sh_red[2 * g], s1);
-    atomicAdd(&sh_red[2 * g + 1], s2);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh_dg[cv * 8 + j], dg[j]);
-      atomicAdd(&sh_db[cv * 8 + j], db[j]);
+      atomicAdd(&sh_s0[cv * 8 + j], s0[j]);
+      atomicAdd(&sh_s1[cv * 8 + j], s1[j]);
     }
   }
   __syncthreads();
-  if (tid < 2 * G) atomicAdd(&red[(long long)n * 2 * G + tid], sh_red[tid]);
   for (int c = tid; c < C; c += kNT) {
-    atomicAdd(&dgamma[c], sh_dg[c]);
-    atomicAdd(&dbeta[c], sh_db[c]);
+    const int g = c / cpg;
+    const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
+    const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+    const float rstd = rsqrtf(var + eps);
+    const float v0 = sh_s0[c];
+    const float vg = rstd * (sh_s1[c] - mean * v0);    // sum dz * xhat
+    atomicAdd(&dbeta[c], v0);
+    atomicAdd(&dgamma[c], vg);
+    const float ga = gamma[c];
+    atomicAdd(&sh_red[2 * g], ga * v0);
+    atomicAdd(&sh_red[2 * g + 1], ga * vg);
   }
+  __syncthreads();
+  if (tid < 2 * G) atomicAdd(&red[(long long)n * 2 * G + tid], sh_red[tid]);
 }
 
-// backward pass 2: dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat))   (+= if accumulate)
-// Optionally also emits the column sums of dx (what the timestep row-vector / conv bias
-// gradients need) so the caller does not re-read dx: csum_img[n][c] and csum_tot[c].
+// pass 2: dx (+= if accumulate); optionally the column sums of dx (csum_img[n][c], csum_tot[c]).
 __global__ void __launch_bounds__(kNT)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                     const __nv_bfloat16* __restrict__ dy, long long dps, int HW, int C, int G,
@@ -237,9 +246,15 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
     const float rstd = rsqrtf(var + eps);
     const float m1 = red[(long long)n * 2 * G + 2 * g] / cnt;
     const float m2 = red[(long long)n * 2 * G + 2 * g + 1] / cnt;
-    float ga[8], be[8], cs[8];
+    const float c2 = rstd * rstd * m2;
+    const float c3 = mean * c2 - rstd * m1;
+    float a[8], b[8], cs[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { ga[j] = gamma[cv * 8 + j]; be[j] = beta[cv * 8 + j]; cs[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) {
+      a[j] = rstd * gamma[cv * 8 + j];
+      b[j] = beta[cv * 8 + j] - mean * a[j];
+      cs[j] = 0.f;
+    }
     const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
     const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
     __nv_bfloat16* ob = dx + (long long)n * HW * dxps + cv * 8;
@@ -260,14 +275,9 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
         if (k == 1 && !two) break;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (f[k][j] - mean) * rstd;
-          float dz = d[k][j];
-          if (silu) {
-            const float z = xh * ga[j] + be[j];
-            const float sg = sigmoid_fast(z);
-            dz *= sg * (1.f + z * (1.f - sg));
-          }
-          const float v = rstd * (dz * ga[j] - m1 - xh * m2);
+          const float xv = f[k][j];
+          const float dz = silu ? silu_grad_times(d[k][j], xv * a[j] + b[j]) : d[k][j];
+          const float v = dz * a[j] + (c3 - xv * c2);
           cs[j] += v;
           o[k][j] = accumulate ? o[k][j] + v : v;
         }
