@@ -153,10 +153,12 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  extern __shared__ float shm[];   // [2*G] + [2*C]
+  extern __shared__ float shm[];   // [2*G] + [2*C] + 2 * [rows*C]
   float* sh_red = shm;
   float* sh_s0 = shm + 2 * G;
   float* sh_s1 = sh_s0 + C;
+  float* part0 = sh_s1 + C;
+  float* part1 = part0 + rows * C;
   for (int i = tid; i < 2 * G + 2 * C; i += kNT) shm[i] = 0.f;
   __syncthreads();
   const float cnt = (float)HW * (float)cpg;
@@ -196,11 +198,19 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
         }
       }
     }
+    // conflict-free partials: part[r][c] (rows x C floats = 8 KB per quantity), then a column sum
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh_s0[cv * 8 + j], s0[j]);
-      atomicAdd(&sh_s1[cv * 8 + j], s1[j]);
+      part0[r * C + cv * 8 + j] = s0[j];
+      part1[r * C + cv * 8 + j] = s1[j];
     }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kNT) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int rr = 0; rr < rows; ++rr) { t0 += part0[rr * C + c]; t1 += part1[rr * C + c]; }
+    sh_s0[c] = t0;
+    sh_s1[c] = t1;
   }
   __syncthreads();
   for (int c = tid; c < C; c += kNT) {
@@ -231,7 +241,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  extern __shared__ float sh_cs[];   // [C] when column sums are requested
+  extern __shared__ float sh_cs[];   // [C] + [rows*C] when column sums are requested
   const bool want_cs = (csum_img != nullptr) || (csum_tot != nullptr);
   if (want_cs) {
     for (int i = tid; i < C; i += kNT) sh_cs[i] = 0.f;
@@ -286,13 +296,14 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
     }
     if (want_cs) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sh_cs[cv * 8 + j], cs[j]);
+      for (int j = 0; j < 8; ++j) sh_cs[C + r * C + cv * 8 + j] = cs[j];
     }
   }
   if (want_cs) {
     __syncthreads();
     for (int c = tid; c < C; c += kNT) {
-      const float v = sh_cs[c];
+      float v = 0.f;
+      for (int rr = 0; rr < rows; ++rr) v += sh_cs[C + rr * C + c];
       if (csum_img) atomicAdd(&csum_img[(long long)n * C + c], v);
       if (csum_tot) atomicAdd(&csum_tot[c], v);
     }
@@ -453,14 +464,14 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
               "groupnorm_bwd: shape mismatch");
   cudaStream_t st = (cudaStream_t)stream;
   FDX_CUDA(cudaMemsetAsync(red, 0, sizeof(float) * 2 * groups * x->n, st));
-  const size_t shm = sizeof(float) * (2 * groups + 2 * x->c);
+  const size_t shm = sizeof(float) * (2 * groups + 2 * x->c + 2 * (kNT / (x->c / 8)) * x->c);
   gn_bwd_stats_kernel<<<gn_grid(x, 2), kNT, shm, st>>>(
       (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride,
       x->h * x->w, x->c, groups, stats, gamma, beta, eps, silu, red, dgamma, dbeta);
   FDX_LAUNCH_CHECK();
   if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * x->n * x->c, st));
   if (csum_tot) FDX_CUDA(cudaMemsetAsync(csum_tot, 0, sizeof(float) * x->c, st));
-  const size_t shm2 = (csum_img || csum_tot) ? sizeof(float) * x->c : 0;
+  const size_t shm2 = (csum_img || csum_tot) ? sizeof(float) * (x->c + (kNT / (x->c / 8)) * x->c) : 0;
   gn_bwd_apply_kernel<<<gn_grid(x, 2), kNT, shm2, st>>>(
       (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride,
       x->h * x->w, x->c, groups, stats, red, gamma, beta, eps, silu, (__nv_bfloat16*)dx->ptr,

@@ -26,9 +26,14 @@ constexpr int kABytes = 128 * kBK * 2;  // 16 KB per stage for A in every mode
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = (BN == 64) ? 8 : (BN == 128) ? 6 : 4;   // BN = 192, 256: 4
+  // K chunks (64 deep) per pipeline stage.  At BN = 64 one chunk is only 4 MMAs = 128 tensor
+  // cycles, less than the ~150-200 cycles the single producer / issuer threads spend per stage
+  // on mbarrier try_wait + TMA / MMA issue (ncu: tensor pipe 22 % active), so two chunks share
+  // a stage there.  Not used by the MN-major-A (weight-gradient) mode.
+  static constexpr int kSub = (BN == 64) ? 2 : 1;
+  static constexpr int kStages = (BN == 64) ? 4 : (BN == 128) ? 6 : 4;
   static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = kSub * (kABytes + kBBytes);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
@@ -92,6 +97,8 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   constexpr int S = Cfg::kStages;
   constexpr bool A_MN = (MODE == TC_MNMN);
   constexpr bool B_MN = (MODE != TC_KK);
+  constexpr int SUB = A_MN ? 1 : Cfg::kSub;    // K chunks per stage (producer view)
+  constexpr int SUBK = SUB;                     // same, issuer view
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -146,14 +153,18 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           const int nb = mt / (p.nxb * p.nyb);
           const int x0 = xb * p.TW * p.es, y0 = yb * p.TH * p.es, n0 = nb * p.TN;
           const int zb1 = p.b_batched ? yb : 0, zb2 = p.b_batched ? nb : 0;
-          for (int t = 0; t < p.ntaps; ++t) {
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              mbar_wait(&empty[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * Cfg::kStageBytes;
-              uint8_t* sb = sa + kABytes;
-              mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-              tma_load_4d(sa, &mapA, &full[stage], kc * kBK, x0 + p.tap_dx[t], y0 + p.tap_dy[t],
-                          n0);
+          const int nk = p.ntaps * p.kchunks;
+          for (int q = 0; q < nk; q += SUB) {
+            const int nsub = (nk - q) < SUB ? (nk - q) : SUB;
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa0 = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb0 = sa0 + SUB * kABytes;
+            mbar_arrive_expect_tx(&full[stage], nsub * (kABytes + Cfg::kBBytes));
+            for (int u = 0; u < nsub; ++u) {
+              const int t = (q + u) / p.kchunks, kc = (q + u) % p.kchunks;
+              uint8_t* sa = sa0 + u * kABytes;
+              uint8_t* sb = sb0 + u * Cfg::kBBytes;
+              tma_load_4d(sa, &mapA, &full[stage], kc * kBK, x0 + p.tap_dx[t], y0 + p.tap_dy[t], n0);
               if constexpr (!B_MN) {
                 // B K-major: box (64 k, BN rows); tap selects z1 (or batched z1/z2)
                 tma_load_4d(sb, &mapB, &full[stage], kc * kBK, nt * BN,
@@ -165,8 +176,8 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                   tma_load_4d(sb + j * (kBK * 128), &mapB, &full[stage], nt * BN + j * 64,
                               p.tap_b[t] + kc * kBK, zb1, zb2);
               }
-              if (++stage == S) { stage = 0; phase ^= 1; }
             }
+            if (++stage == S) { stage = 0; phase ^= 1; }
           }
         } else {
           const MnTile mt_ = decode_mn(p, tile);
@@ -181,7 +192,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + kABytes;
-            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+            mbar_arrive_expect_tx(&full[stage], kABytes + Cfg::kBBytes);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               // tpp == 1: the two 64-channel halves of row block mb for tap t
@@ -221,20 +232,25 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int i = 0; i < nk; ++i) {
+        for (int q = 0; q < nk; q += SUBK) {
+          const int nsub = (nk - q) < SUBK ? (nk - q) : SUBK;
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t sa0 = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb0 = sa0 + SUBK * kABytes;
+          for (int u = 0; u < nsub; ++u) {
+            const uint32_t sa = sa0 + u * kABytes;
+            const uint32_t sb = sb0 + u * Cfg::kBBytes;
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // K-major: advance 16 elements (32 B) inside the 128B swizzle row; SBO = 8 rows.
-            // MN-major: advance 16 k-rows (2048 B); LBO = next 64-wide block, SBO = 8 rows.
-            const uint64_t da = A_MN ? umma_desc_sw128(sa + k * 2048, kBK * 128, 1024)
-                                     : umma_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, kBK * 128, 1024)
-                                     : umma_desc_sw128(sb + k * 32, 16, 1024);
-            umma_f16(d_tmem, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // K-major: advance 16 elements (32 B) inside the 128B swizzle row; SBO = 8 rows.
+              // MN-major: advance 16 k-rows (2048 B); LBO = next 64-wide block, SBO = 8 rows.
+              const uint64_t da = A_MN ? umma_desc_sw128(sa + k * 2048, kBK * 128, 1024)
+                                       : umma_desc_sw128(sa + k * 32, 16, 1024);
+              const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, kBK * 128, 1024)
+                                       : umma_desc_sw128(sb + k * 32, 16, 1024);
+              umma_f16(d_tmem, da, db, idesc, ((q + u) | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);   // frees the smem stage when these MMAs retire
           if (++stage == S) { stage = 0; phase ^= 1; }

@@ -152,7 +152,11 @@ fdx_wgrad9_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           tmem_ld_wait();
           if (valid && ob * 64 + c0 < p.Cout) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(out + c0 + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c0 + j),
+                           "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                           "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
           }
         }
       }
