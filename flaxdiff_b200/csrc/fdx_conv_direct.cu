@@ -201,9 +201,73 @@ cout3_dgrad_kernel(const float* __restrict__ dF, const float* __restrict__ w, in
   }
 }
 
+// ---- im2col of a 3-channel tensor: col[p][t*3+k] = S[p + sgn*d(t)][k] (0 outside), bf16 [P][32];
+//      column 27 optionally = 1 (bias row), columns 28..31 = 0.  Feeds the tcgen05 engine so the two
+//      3-channel weight gradients are (pixels x 32)^T (pixels x 64) GEMMs instead of CUDA-core loops.
+template <bool SMALL_F32>
+__global__ void __launch_bounds__(256)
+im2col3_kernel(const void* __restrict__ src_, int sgn, int N, int H, int W, int ones_col,
+               __nv_bfloat16* __restrict__ col) {
+  const long long npix = (long long)N * H * W;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(p % W);
+    const int py = (int)((p / W) % H);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int sy = py + sgn * (ky - 1);
+      if (sy < 0 || sy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int sx = px + sgn * (kx - 1);
+        if (sx < 0 || sx >= W) continue;
+        const long long sp = p + (long long)sgn * ((ky - 1) * W + (kx - 1));
+        const int t = ky * 3 + kx;
+        if (SMALL_F32) {
+          const float* sm = static_cast<const float*>(src_) + sp * 3;
+          v[t * 3] = sm[0]; v[t * 3 + 1] = sm[1]; v[t * 3 + 2] = sm[2];
+        } else {
+          const __nv_bfloat16* sm = static_cast<const __nv_bfloat16*>(src_) + sp * 3;
+          v[t * 3] = __bfloat162float(sm[0]); v[t * 3 + 1] = __bfloat162float(sm[1]);
+          v[t * 3 + 2] = __bfloat162float(sm[2]);
+        }
+      }
+    }
+    if (ones_col) v[27] = 1.f;
+    uint4* o = reinterpret_cast<uint4*>(col + p * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 u;
+      u.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+      u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      o[j] = u;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int fdx_im2col3x3_c3(const void* src, int src_is_f32, int sgn, int N, int H, int W, int ones_col,
+                     void* col_bf16, void* stream) {
+  FDX_REQUIRE(src && col_bf16, "im2col3x3_c3: null pointer");
+  FDX_REQUIRE(sgn == 1 || sgn == -1, "im2col3x3_c3: sgn must be +1 or -1");
+  const long long npix = (long long)N * H * W;
+  long long grid = (npix + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (src_is_f32)
+    im2col3_kernel<true><<<(int)grid, 256, 0, (cudaStream_t)stream>>>(src, sgn, N, H, W, ones_col,
+                                                                      (__nv_bfloat16*)col_bf16);
+  else
+    im2col3_kernel<false><<<(int)grid, 256, 0, (cudaStream_t)stream>>>(src, sgn, N, H, W, ones_col,
+                                                                       (__nv_bfloat16*)col_bf16);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
 
 int fdx_conv_in_fwd(const void* x_bf16, int N, int H, int W, const float* w_hwio,
                     const float* bias, const fdx_act* y, void* stream) {

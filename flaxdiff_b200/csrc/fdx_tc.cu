@@ -17,6 +17,8 @@
 //               fuse bias + per-image timestep vector + residual, store bf16/f32
 //               (or f32 atomics for the split-K weight gradient).
 #include "fdx_tc.cuh"
+#include "fdx_epilogue.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -34,7 +36,8 @@ struct TcCfg {
   static constexpr int kStages = (BN == 64) ? 4 : (BN == 128) ? 6 : 4;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kSub * (kABytes + kBBytes);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
+                                    16384 /*epilogue staging: 4 warps x 4 KB*/;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -109,6 +112,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * S;   // [2]
   uint64_t* tempty = bars + 2 * S + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  uint8_t* epi_stage = smem + S * Cfg::kStageBytes + 256;   // 16 KB, 128-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -301,6 +305,12 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if (!A_MN && !p.out_f32 && !p.out_atomic) {
+        // bf16 output: stage through shared memory so global stores / residual loads are coalesced
+        EpiArgs ea{p.out, p.bias, p.rowvec, p.res, p.Ncols, p.alpha};
+        epilogue_bf16_coalesced<BN>(ea, epi_stage + q * 4096, t_addr, lane, nt * BN, valid && has_acc, obase,
+                                    rbase, img);
+      } else
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -461,6 +471,12 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
   d.nnb = (L.N + TN - 1) / TN;
   const long long pix_blocks = (long long)d.nxb * d.nyb * d.nnb;
 
+  // halo-sharing variant: fewer TMA writes, but measured slower than the generic kernel on B200
+  // (both are shared-memory-bandwidth bound); kept as an opt-in experiment.
+  if (L.mode != TC_MNMN && getenv("FDX_CONV3")) {
+    const int r3 = fdx_conv3_launch(L, BN, stream);
+    if (r3 != FDX_ERR_UNSUPPORTED) return r3;
+  }
   if (L.mode != TC_MNMN) {
     while (BN > 64 && pix_blocks * ((L.Ncols + BN - 1) / BN) < 2LL * fdx_num_sms())
       BN = (BN == 192) ? 64 : BN / 2;

@@ -277,7 +277,30 @@ def conv_in_fwd(x_bf16: torch.Tensor, w: torch.Tensor, bias, out: torch.Tensor) 
     return out
 
 
+def im2col3(src: torch.Tensor, sgn: int, ones_col: bool) -> torch.Tensor:
+    n, h, w, c = src.shape
+    assert c == 3 and src.is_contiguous() and src.dtype in (torch.float32, torch.bfloat16)
+    col = torch.empty((n * h * w, 32), dtype=torch.bfloat16, device=src.device)
+    check(load().fdx_im2col3x3_c3(ptr(src), ctypes.c_int(1 if src.dtype == torch.float32 else 0),
+                                  ctypes.c_int(sgn), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w),
+                                  ctypes.c_int(1 if ones_col else 0), ptr(col), stream_ptr()), "im2col3x3_c3")
+    return col
+
+
 def conv_in_wgrad(x_bf16, dy, dw, dbias):
+    """dW[t][cs][co] (+ bias row) = im2col(x)^T @ dY on the tensor cores; accumulates into dw / dbias."""
+    n, h, w, cout = dy.shape
+    P = n * h * w
+    col = im2col3(x_bf16, +1, True)
+    tmp = torch.zeros((32, cout), dtype=torch.float32, device=dy.device)
+    gemm(GEMM_MNMN, col, dy, tmp, 32, cout, P, 32, dy.stride(2), cout, atomic=True, reduce_batch=True)
+    dw.view(27, cout).add_(tmp[:27])
+    if dbias is not None:
+        dbias.add_(tmp[27])
+
+
+def conv_in_wgrad_direct(x_bf16, dy, dw, dbias):
+    """Workspace-free CUDA-core variant (fdx_conv_in_wgrad)."""
     check(load().fdx_conv_in_wgrad(ptr(x_bf16), ctypes.byref(act(dy, "dy")), ptr(dw), ptr(dbias),
                                    stream_ptr()), "conv_in_wgrad")
 
@@ -297,6 +320,20 @@ def conv_out_dgrad(dF: torch.Tensor, w: torch.Tensor, dx: torch.Tensor) -> torch
 
 
 def conv_out_wgrad(x, dF, dw, dbias):
+    """dW[t][ci][k] = x^T @ im2col(dF) on the tensor cores; accumulates into dw / dbias."""
+    n, h, w, cin = x.shape
+    P = n * h * w
+    col = im2col3(dF, -1, False)
+    tmp = torch.zeros((cin, 32), dtype=torch.float32, device=x.device)
+    gemm(GEMM_MNMN, x, col, tmp, cin, 32, P, x.stride(2), 32, 32, atomic=True, reduce_batch=True)
+    dw.add_(tmp[:, :27].view(cin, 9, 3).permute(1, 0, 2).reshape(3, 3, cin, 3))
+    if dbias is not None:
+        cs = colsum(col.view(n, h, w, 32), per_image=False)
+        dbias.add_(cs[12:15])        # centre tap (t = 4) columns = sum over pixels of dF
+
+
+def conv_out_wgrad_direct(x, dF, dw, dbias):
+    """Workspace-free CUDA-core variant (fdx_conv_out_wgrad)."""
     check(load().fdx_conv_out_wgrad(ctypes.byref(act(x, "x")), ptr(dF), ptr(dw), ptr(dbias),
                                     stream_ptr()), "conv_out_wgrad")
 

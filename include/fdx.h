@@ -135,6 +135,11 @@ int fdx_conv_in_fwd(const void* x_bf16, int N, int H, int W, const float* w_hwio
                     const float* bias, const fdx_act* y, void* stream);
 int fdx_conv_in_wgrad(const void* x_bf16, const fdx_act* dy, float* dw_hwio, float* dbias,
                       void* stream);
+/* im2col of a 3-channel tensor for the two weight gradients above/below as tensor-core GEMMs:
+ * col[p][t*3+k] = src[p + sgn*d(t)][k] (zero outside the image), bf16 [N*H*W][32]; column 27 = 1 if
+ * ones_col (bias row).  dW_in = col^T dY ; dW_out = x^T col (via fdx_gemm MNMN). */
+int fdx_im2col3x3_c3(const void* src, int src_is_f32, int sgn, int N, int H, int W, int ones_col,
+                     void* col_bf16, void* stream);
 /* conv_out Cin->3 (models/simple_unet.py:212-221): y f32 [N,H,W,3] dense. */
 int fdx_conv_out_fwd(const fdx_act* x, const float* w_hwio, const float* bias, float* y_f32,
                      void* stream);

@@ -192,8 +192,14 @@ def test_conv_in_out_and_grads():
     ops.conv_out_dgrad(dF, w_out, da)
     assert rel(da, ar.grad) < 5e-3
     dwo, dbo = torch.zeros_like(w_out), torch.zeros_like(b_out)
-    ops.conv_out_wgrad(a, dF, dwo, dbo)
-    assert rel(dwo, wo.grad) < 1e-4 and rel(dbo, bo.grad) < 1e-4
+    ops.conv_out_wgrad(a, dF, dwo, dbo)          # im2col + tcgen05 GEMM (dF rounded to bf16)
+    assert rel(dwo, wo.grad) < 5e-3 and rel(dbo, bo.grad) < 5e-3
+    dwo2, dbo2 = torch.zeros_like(w_out), torch.zeros_like(b_out)
+    ops.conv_out_wgrad_direct(a, dF, dwo2, dbo2)  # CUDA-core variant, f32 dF
+    assert rel(dwo2, wo.grad) < 1e-4 and rel(dbo2, bo.grad) < 1e-4
+    dw2, dbi2 = torch.zeros_like(w_in), torch.zeros_like(b_in)
+    ops.conv_in_wgrad_direct(x, dy, dw2, dbi2)
+    assert rel(dw2, wr.grad) < 1e-4 and rel(dbi2, br.grad) < 1e-4
 
 
 def test_time_embedding_fwd_bwd():
