@@ -50,7 +50,8 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
         if (ok && (piece < 4 || half2))
           u = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(e.res) + rb + col0 + piece * 8);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + epi_swz(r, piece)), "r"(u.x),
-                     "r"(u.y), "r"(u.z), "r"(u.w));
+                     "r"(u.y), "r"(u.z), "r"(u.w)
+                     : "memory");
       }
       __syncwarp();
     }
@@ -73,7 +74,9 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
         }
       }
       if (e.rowvec) {
-        const float4* r4 = reinterpret_cast<const float4*>(e.rowvec + (long long)img * e.Ncols + col0 + h * 32);
+        // rows outside the tensor (tile padding) must not index the per-image vector
+        const float4* r4 =
+            reinterpret_cast<const float4*>(e.rowvec + (long long)(valid ? img : 0) * e.Ncols + col0 + h * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b = __ldg(r4 + j);
@@ -86,7 +89,8 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
         if (e.res) {
           uint4 u;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-                       : "r"(addr));
+                       : "r"(addr)
+                       : "memory");
           const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
                        d = unpack_bf16x2(u.w);
           f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
@@ -94,7 +98,8 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
         }
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
                      "r"(pack_bf16x2(f[8 * j + 0], f[8 * j + 1])), "r"(pack_bf16x2(f[8 * j + 2], f[8 * j + 3])),
-                     "r"(pack_bf16x2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_bf16x2(f[8 * j + 6], f[8 * j + 7])));
+                     "r"(pack_bf16x2(f[8 * j + 4], f[8 * j + 5])), "r"(pack_bf16x2(f[8 * j + 6], f[8 * j + 7]))
+                     : "memory");
       }
     }
     __syncwarp();
@@ -106,7 +111,8 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
       const int ok = __shfl_sync(0xffffffffu, (int)valid, r);
       uint4 u;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-                   : "r"(sbase + epi_swz(r, piece)));
+                   : "r"(sbase + epi_swz(r, piece))
+                   : "memory");
       if (ok && (piece < 4 || half2))
         *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(e.out) + ob + col0 + piece * 8) = u;
     }

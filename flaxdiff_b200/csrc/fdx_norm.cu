@@ -148,19 +148,13 @@ __global__ void __launch_bounds__(kNT)
 gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                     const __nv_bfloat16* __restrict__ dy, long long dps, int HW, int C, int G,
                     const float* __restrict__ stats, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, float eps, int silu, float* __restrict__ red,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                    const float* __restrict__ beta, float eps, int silu, float* __restrict__ ws) {
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  extern __shared__ float shm[];   // [2*G] + [2*C] + 2 * [rows*C]
-  float* sh_red = shm;
-  float* sh_s0 = shm + 2 * G;
-  float* sh_s1 = sh_s0 + C;
-  float* part0 = sh_s1 + C;
+  extern __shared__ float shm[];   // 2 * [rows*C]
+  float* part0 = shm;
   float* part1 = part0 + rows * C;
-  for (int i = tid; i < 2 * G + 2 * C; i += kNT) shm[i] = 0.f;
-  __syncthreads();
   const float cnt = (float)HW * (float)cpg;
   if (tid < rows * vpp) {
     const int cv = tid % vpp, r = tid / vpp;
@@ -206,28 +200,91 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
     }
   }
   __syncthreads();
+  // per-(image, channel) partial sums: only gridDim.x (<= ~10) atomics ever hit one address
   for (int c = tid; c < C; c += kNT) {
     float t0 = 0.f, t1 = 0.f;
     for (int rr = 0; rr < rows; ++rr) { t0 += part0[rr * C + c]; t1 += part1[rr * C + c]; }
-    sh_s0[c] = t0;
-    sh_s1[c] = t1;
+    atomicAdd(&ws[((long long)n * C + c) * 2], t0);
+    atomicAdd(&ws[((long long)n * C + c) * 2 + 1], t1);
   }
-  __syncthreads();
-  for (int c = tid; c < C; c += kNT) {
-    const int g = c / cpg;
+}
+
+// finalize: blocks [0, cb) reduce over images -> dgamma / dbeta (accumulated into the gradient
+// buffers), 32 channels x 8 image lanes per block; blocks [cb, cb + gb) reduce over the channels of
+// a group -> red[n][g], one warp per (image, group).
+__global__ void __launch_bounds__(256)
+gn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ stats,
+                       const float* __restrict__ gamma, int N, int HW, int C, int G, float eps, int cb,
+                       float* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int cpg = C / G;
+  const float cnt = (float)HW * (float)cpg;
+  __shared__ float sh0[8][33], sh1[8][33];
+  if ((int)blockIdx.x < cb) {
+    const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    float a0 = 0.f, a1 = 0.f;
+    if (c < C) {
+      const int g = c / cpg;
+      for (int n = nl; n < N; n += 8) {
+        const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
+        const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+        const float rstd = rsqrtf(var + eps);
+        const float2 s = *reinterpret_cast<const float2*>(ws + ((long long)n * C + c) * 2);
+        a0 += s.x;
+        a1 += rstd * (s.y - mean * s.x);
+      }
+    }
+    sh0[nl][cl] = a0;
+    sh1[nl][cl] = a1;
+    __syncthreads();
+    if (nl == 0 && c < C) {
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { t0 += sh0[k][cl]; t1 += sh1[k][cl]; }
+      dbeta[c] += t0;
+      dgamma[c] += t1;
+    }
+  } else {
+    const int i = (blockIdx.x - cb) * 8 + (threadIdx.x >> 5);     // (n, g), one warp each
+    if (i >= N * G) return;
+    const int lane = threadIdx.x & 31;
+    const int n = i / G, g = i % G;
     const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
     const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
     const float rstd = rsqrtf(var + eps);
-    const float v0 = sh_s0[c];
-    const float vg = rstd * (sh_s1[c] - mean * v0);    // sum dz * xhat
-    atomicAdd(&dbeta[c], v0);
-    atomicAdd(&dgamma[c], vg);
-    const float ga = gamma[c];
-    atomicAdd(&sh_red[2 * g], ga * v0);
-    atomicAdd(&sh_red[2 * g + 1], ga * vg);
+    float r0 = 0.f, r1 = 0.f;
+    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+      const float2 s = *reinterpret_cast<const float2*>(ws + ((long long)n * C + c) * 2);
+      const float ga = gamma[c];
+      r0 += ga * s.x;
+      r1 += ga * rstd * (s.y - mean * s.x);
+    }
+    r0 = warp_sum(r0);
+    r1 = warp_sum(r1);
+    if (lane == 0) {
+      red[(long long)n * 2 * G + 2 * g] = r0;
+      red[(long long)n * 2 * G + 2 * g + 1] = r1;
+    }
   }
+}
+
+// out[c] (+)= sum_r in[r][c]; 32 columns x 8 row lanes per block
+__global__ void __launch_bounds__(256)
+reduce_rows_kernel(const float* __restrict__ in, int R, int C, float* __restrict__ out, int accumulate) {
+  __shared__ float sh[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float a = 0.f;
+  if (c < C)
+    for (int r = rl; r < R; r += 8) a += in[(long long)r * C + c];
+  sh[rl][cl] = a;
   __syncthreads();
-  if (tid < 2 * G) atomicAdd(&red[(long long)n * 2 * G + tid], sh_red[tid]);
+  if (rl == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][cl];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 // pass 2: dx (+= if accumulate); optionally the column sums of dx (csum_img[n][c], csum_tot[c]).
@@ -237,12 +294,12 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                     const float* __restrict__ stats, const float* __restrict__ red,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                     int silu, __nv_bfloat16* __restrict__ dx, long long dxps, int accumulate,
-                    float* __restrict__ csum_img, float* __restrict__ csum_tot) {
+                    float* __restrict__ csum_img) {
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
   extern __shared__ float sh_cs[];   // [C] + [rows*C] when column sums are requested
-  const bool want_cs = (csum_img != nullptr) || (csum_tot != nullptr);
+  const bool want_cs = (csum_img != nullptr);
   if (want_cs) {
     for (int i = tid; i < C; i += kNT) sh_cs[i] = 0.f;
     __syncthreads();
@@ -304,8 +361,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
     for (int c = tid; c < C; c += kNT) {
       float v = 0.f;
       for (int rr = 0; rr < rows; ++rr) v += sh_cs[C + rr * C + c];
-      if (csum_img) atomicAdd(&csum_img[(long long)n * C + c], v);
-      if (csum_tot) atomicAdd(&csum_tot[c], v);
+      atomicAdd(&csum_img[(long long)n * C + c], v);
     }
   }
 }
@@ -453,30 +509,41 @@ int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const 
 }
 
 int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
-                      const float* gamma, const float* beta, float eps, int silu, float* red,
+                      const float* gamma, const float* beta, float eps, int silu, float* ws,
                       float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
                       float* csum_img, float* csum_tot, void* stream) {
   int s = gn_check(x, groups, "groupnorm_bwd");
   if (s != FDX_OK) return s;
-  FDX_REQUIRE(dy && dy->ptr && dx && dx->ptr, "groupnorm_bwd: null tensor");
+  FDX_REQUIRE(dy && dy->ptr && dx && dx->ptr && ws, "groupnorm_bwd: null tensor");
   FDX_REQUIRE(dy->c == x->c && dx->c == x->c && dy->n == x->n && dx->n == x->n &&
                   dy->h == x->h && dy->w == x->w && dx->h == x->h && dx->w == x->w,
               "groupnorm_bwd: shape mismatch");
+  FDX_REQUIRE(!csum_tot || csum_img, "groupnorm_bwd: csum_tot needs csum_img");
   cudaStream_t st = (cudaStream_t)stream;
-  FDX_CUDA(cudaMemsetAsync(red, 0, sizeof(float) * 2 * groups * x->n, st));
-  const size_t shm = sizeof(float) * (2 * groups + 2 * x->c + 2 * (kNT / (x->c / 8)) * x->c);
+  const int N = x->n, C = x->c, HW = x->h * x->w;
+  float* sums = ws;                         // [N][C][2]
+  float* red = ws + 2LL * N * C;            // [N][G][2]
+  FDX_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, st));
+  const size_t shm = sizeof(float) * 2 * (kNT / (C / 8)) * C;
   gn_bwd_stats_kernel<<<gn_grid(x, 2), kNT, shm, st>>>(
-      (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride,
-      x->h * x->w, x->c, groups, stats, gamma, beta, eps, silu, red, dgamma, dbeta);
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, HW, C,
+      groups, stats, gamma, beta, eps, silu, sums);
   FDX_LAUNCH_CHECK();
-  if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * x->n * x->c, st));
-  if (csum_tot) FDX_CUDA(cudaMemsetAsync(csum_tot, 0, sizeof(float) * x->c, st));
-  const size_t shm2 = (csum_img || csum_tot) ? sizeof(float) * (x->c + (kNT / (x->c / 8)) * x->c) : 0;
+  const int cb = (C + 31) / 32, gb = (N * groups + 7) / 8;
+  gn_bwd_finalize_kernel<<<cb + gb, 256, 0, st>>>(sums, stats, gamma, N, HW, C, groups, eps, cb, red, dgamma,
+                                                   dbeta);
+  FDX_LAUNCH_CHECK();
+  if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * N * C, st));
+  const size_t shm2 = csum_img ? sizeof(float) * (C + (kNT / (C / 8)) * C) : 0;
   gn_bwd_apply_kernel<<<gn_grid(x, 2), kNT, shm2, st>>>(
-      (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride,
-      x->h * x->w, x->c, groups, stats, red, gamma, beta, eps, silu, (__nv_bfloat16*)dx->ptr,
-      dx->pix_stride, accumulate, csum_img, csum_tot);
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, HW, C,
+      groups, stats, red, gamma, beta, eps, silu, (__nv_bfloat16*)dx->ptr, dx->pix_stride, accumulate,
+      csum_img);
   FDX_LAUNCH_CHECK();
+  if (csum_tot) {
+    reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(csum_img, N, C, csum_tot, 0);
+    FDX_LAUNCH_CHECK();
+  }
   return FDX_OK;
 }
 

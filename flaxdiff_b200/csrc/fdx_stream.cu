@@ -323,46 +323,59 @@ __global__ void act_add_kernel(const __nv_bfloat16* __restrict__ a, long long ap
   }
 }
 
-// per-image (or whole-batch) column sums of an NHWC bf16 tensor -> f32 atomics
+// per-image (or whole-batch) column sums of an NHWC bf16 tensor -> f32 atomics.
+// Whole-batch mode (out_img_stride == 0): gridDim.y < N and every block walks several images, so each
+// output address sees at most ~300 atomics instead of one per (image, pixel block).
 __global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ x, long long xps, int HW, int C,
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long xps, int N, int HW, int C,
               float* __restrict__ out, long long out_img_stride) {
   const int vpp = C >> 3, rows = 256 / vpp;
-  const int n = blockIdx.y, tid = threadIdx.x;
-  extern __shared__ float sh[];   // [C]
-  for (int i = tid; i < C; i += 256) sh[i] = 0.f;
-  __syncthreads();
-  if (tid < rows * vpp) {
-    const int cv = tid % vpp, r = tid / vpp;
+  const int tid = threadIdx.x;
+  extern __shared__ float sh[];   // [rows*C]
+  const int cv = tid % vpp, r = tid / vpp;
+  const bool live = tid < rows * vpp;
+  const int stride = gridDim.x * rows;
+  for (int n0 = blockIdx.y; n0 < N; n0 += gridDim.y) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const __nv_bfloat16* base = x + (long long)n * HW * xps + cv * 8;
-    const int stride = gridDim.x * rows;
-    int p = blockIdx.x * rows + r;
-    for (; p + 3 * stride < HW; p += 4 * stride) {
-      uint4 u[4];
+    const int n_end = out_img_stride ? n0 + 1 : N;
+    const int n_step = out_img_stride ? 1 : gridDim.y;
+    if (live) {
+      for (int n = n0; n < n_end; n += n_step) {
+        const __nv_bfloat16* base = x + (long long)n * HW * xps + cv * 8;
+        int p = blockIdx.x * rows + r;
+        for (; p + 3 * stride < HW; p += 4 * stride) {
+          uint4 u[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        u[k] = *reinterpret_cast<const uint4*>(base + (long long)(p + k * stride) * xps);
+          for (int k = 0; k < 4; ++k)
+            u[k] = *reinterpret_cast<const uint4*>(base + (long long)(p + k * stride) * xps);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), c = unpack_bf16x2(u[k].z),
-               d = unpack_bf16x2(u[k].w);
-        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+          for (int k = 0; k < 4; ++k) {
+            float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), c = unpack_bf16x2(u[k].z),
+                   d = unpack_bf16x2(u[k].w);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+            acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+          }
+        }
+        for (; p < HW; p += stride) {
+          const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)p * xps);
+          float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+                 d = unpack_bf16x2(u.w);
+          acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+          acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+        }
       }
-    }
-    for (; p < HW; p += stride) {
-      const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)p * xps);
-      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
-             d = unpack_bf16x2(u.w);
-      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
-    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sh[cv * 8 + j], acc[j]);
+      for (int j = 0; j < 8; ++j) sh[r * C + cv * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+      float v = 0.f;
+      for (int rr = 0; rr < rows; ++rr) v += sh[rr * C + c];
+      atomicAdd(&out[(long long)n0 * out_img_stride + c], v);
+    }
+    __syncthreads();
+    if (!out_img_stride) break;     // whole-batch mode consumed all its images in the inner loop
   }
-  __syncthreads();
-  for (int c = tid; c < C; c += 256) atomicAdd(&out[(long long)n * out_img_stride + c], sh[c]);
 }
 
 }  // namespace
@@ -506,8 +519,14 @@ int fdx_colsum(const fdx_act* x, float* out, int per_image, void* stream) {
   if (bx < 1) bx = 1;
   cudaStream_t st = (cudaStream_t)stream;
   FDX_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * x->c * (per_image ? x->n : 1), st));
-  colsum_kernel<<<dim3(bx, x->n), 256, sizeof(float) * x->c, st>>>(
-      (const __nv_bfloat16*)x->ptr, x->pix_stride, HW, x->c, out, per_image ? x->c : 0);
+  int gy = x->n;
+  if (!per_image) {
+    gy = 296 / bx;
+    if (gy < 1) gy = 1;
+    if (gy > x->n) gy = x->n;
+  }
+  colsum_kernel<<<dim3(bx, gy), 256, sizeof(float) * rows * x->c, st>>>(
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, x->n, HW, x->c, out, per_image ? x->c : 0);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

@@ -112,7 +112,7 @@ def groupnorm_apply(x, groups, stats, gamma, beta, eps: float, silu: bool, out=N
 
 def groupnorm_bwd(x, dy, groups, stats, gamma, beta, eps, silu, dgamma, dbeta, dx,
                   accumulate: bool = False, csum_img=None, csum_tot=None) -> torch.Tensor:
-    red = torch.empty((x.shape[0], groups, 2), dtype=torch.float32, device=x.device)
+    red = torch.empty(2 * x.shape[0] * (x.shape[-1] + groups), dtype=torch.float32, device=x.device)
     check(load().fdx_groupnorm_bwd(ctypes.byref(act(x, "x")), ctypes.byref(act(dy, "dy")),
                                    ctypes.c_int(groups), ptr(stats), ptr(gamma), ptr(beta),
                                    ctypes.c_float(eps), ctypes.c_int(1 if silu else 0), ptr(red),

@@ -81,11 +81,11 @@ int fdx_groupnorm_stats(const fdx_act* x, int groups, float* stats, void* stream
 /* y = silu?((x-mean)*rstd*gamma+beta) (models/common.py:286-288,310-312; simple_unet.py:209-210). */
 int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const float* gamma,
                         const float* beta, float eps, int silu, const fdx_act* y, void* stream);
-/* Backward of the pair above. red: [n][g][2] f32 scratch; dgamma/dbeta ACCUMULATED.
- * csum_img [n][c] / csum_tot [c] (either may be NULL): column sums over pixels of the dx this call
- * produces, written (not accumulated) - the timestep row-vector and conv-bias gradients. */
+/* Backward of the pair above.  ws: f32 scratch of 2*N*C + 2*N*groups floats.  dgamma/dbeta ACCUMULATED.
+ * csum_img [n][c] / csum_tot [c] (NULL allowed; csum_tot needs csum_img): column sums over pixels of the
+ * dx this call produces, written (not accumulated) - the timestep row-vector and conv-bias gradients. */
 int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
-                      const float* gamma, const float* beta, float eps, int silu, float* red,
+                      const float* gamma, const float* beta, float eps, int silu, float* ws,
                       float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
                       float* csum_img, float* csum_tot, void* stream);
 /* nn.RMSNorm(eps) over channels (models/attention.py:325-326). C in {256,512,768,1024}. */
