@@ -303,7 +303,8 @@ class Unet:
         for idx, (kind, name, cin, cout) in enumerate(plan):
             if kind == "conv_in":
                 dst = cat_nodes[0][2]
-                ops.conv_in_fwd(x_bf16, W[name + "/conv/kernel"], W[name + "/conv/bias"], dst.t)
+                ops.conv_in_fwd(x_bf16, W[name + "/conv/kernel"], W[name + "/conv/bias"], dst.t,
+                                w_bf16=W16[name + "/conv/kernel"])
                 tape.append(("conv_in", name, x_bf16, dst))
                 pop_stack.append(0)
                 skip_idx = 1
@@ -453,8 +454,9 @@ class Unet:
             if kind == "out":
                 _, _, xin, st, a = rec
                 da = torch.empty_like(a)
-                ops.conv_out_dgrad(dF, W[name + "/conv/kernel"], da)
-                ops.conv_out_wgrad(a, dF, Gd[name + "/conv/kernel"], Gd[name + "/conv/bias"])
+                col = ops.im2col3(dF, -1, False)          # shared by the data and weight gradients
+                ops.conv_out_dgrad(dF, W[name + "/conv/kernel"], da, col=col)
+                ops.conv_out_wgrad(a, dF, Gd[name + "/conv/kernel"], Gd[name + "/conv/bias"], col=col)
                 dx, acc = want(xin)
                 ops.groupnorm_bwd(xin.t, da, G, st, W[self._nout + "/scale"], W[self._nout + "/bias"], OUT_EPS,
                                   True, Gd[self._nout + "/scale"], Gd[self._nout + "/bias"], dx, acc)

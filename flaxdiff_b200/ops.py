@@ -267,7 +267,20 @@ def colsum(x: torch.Tensor, per_image: bool, out: Optional[torch.Tensor] = None)
 
 
 # --------------------------------------------------------------------------- 3-channel convs
-def conv_in_fwd(x_bf16: torch.Tensor, w: torch.Tensor, bias, out: torch.Tensor) -> torch.Tensor:
+def conv_in_fwd(x_bf16: torch.Tensor, w: torch.Tensor, bias, out: torch.Tensor,
+                w_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv_in 3->Cout as im2col (K = 27 padded to 32) + one tcgen05 GEMM with the bias fused."""
+    n, h, w_, c = x_bf16.shape
+    assert c == 3 and x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous()
+    cout = out.shape[-1]
+    col = im2col3(x_bf16, +1, False)
+    wb = w_bf16 if w_bf16 is not None else cast_f32_bf16(w)
+    gemm(GEMM_KMN, col, wb, out, n * h * w_, cout, 27, 32, cout, out.stride(2), bias=bias)
+    return out
+
+
+def conv_in_fwd_direct(x_bf16: torch.Tensor, w: torch.Tensor, bias, out: torch.Tensor) -> torch.Tensor:
+    """Workspace-free CUDA-core variant (fdx_conv_in_fwd)."""
     n, h, w_, c = x_bf16.shape
     assert c == 3 and x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous()
     assert w.dtype == torch.float32 and w.is_contiguous()
@@ -313,17 +326,33 @@ def conv_out_fwd(x: torch.Tensor, w: torch.Tensor, bias) -> torch.Tensor:
     return y
 
 
-def conv_out_dgrad(dF: torch.Tensor, w: torch.Tensor, dx: torch.Tensor) -> torch.Tensor:
+def conv_out_dgrad(dF: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, col: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx[p][ci] = sum_{t,k} dF[p - d(t)][k] w[t][ci][k]: im2col(dF) (shared with the weight gradient)
+    times the (27 x Cin) re-arranged kernel on the tensor cores."""
+    n, h, w_, cin = dx.shape
+    if col is None:
+        col = im2col3(dF, -1, False)
+    wt = w.reshape(9, cin, 3).permute(0, 2, 1).reshape(27, cin).contiguous()      # [(t,k)][ci], 1.7 K elements
+    gemm(GEMM_KMN, col, cast_f32_bf16(_pad4(wt)), dx, n * h * w_, cin, 27, 32, cin, dx.stride(2))
+    return dx
+
+
+def _pad4(t: torch.Tensor) -> torch.Tensor:
+    return t if t.numel() % 4 == 0 else torch.nn.functional.pad(t.reshape(-1), (0, 4 - t.numel() % 4)).reshape(-1)
+
+
+def conv_out_dgrad_direct(dF: torch.Tensor, w: torch.Tensor, dx: torch.Tensor) -> torch.Tensor:
     check(load().fdx_conv_out_dgrad(ptr(dF), ptr(w), ctypes.byref(act(dx, "dx")), stream_ptr()),
           "conv_out_dgrad")
     return dx
 
 
-def conv_out_wgrad(x, dF, dw, dbias):
+def conv_out_wgrad(x, dF, dw, dbias, col: Optional[torch.Tensor] = None):
     """dW[t][ci][k] = x^T @ im2col(dF) on the tensor cores; accumulates into dw / dbias."""
     n, h, w, cin = x.shape
     P = n * h * w
-    col = im2col3(dF, -1, False)
+    if col is None:
+        col = im2col3(dF, -1, False)
     tmp = torch.zeros((cin, 32), dtype=torch.float32, device=x.device)
     gemm(GEMM_MNMN, x, col, tmp, cin, 32, P, x.stride(2), 32, 32, atomic=True, reduce_batch=True)
     dw.add_(tmp[:, :27].view(cin, 9, 3).permute(1, 0, 2).reshape(3, 3, cin, 3))
