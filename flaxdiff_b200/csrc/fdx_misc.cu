@@ -98,14 +98,15 @@ __global__ void dense_wgrad_small_kernel(const float* __restrict__ in, int apply
   if (blockIdx.x == 0) atomicAdd(&db[j], accb);
 }
 
-// ---- softmax over the last dim; one warp per row; S f32 -> P bf16 ---------------------
+// ---- softmax over the last dim; one warp per row; S f32 -> P bf16.  Rows have Lp (padded) columns of
+//      which the first L are real: padded logits are ignored and padded probabilities written as 0.
 __global__ void __launch_bounds__(256)
-softmax_fwd_kernel(const float* __restrict__ S, long long rows, int L, __nv_bfloat16* __restrict__ P) {
+softmax_fwd_kernel(const float* __restrict__ S, long long rows, int L, int Lp, __nv_bfloat16* __restrict__ P) {
   const int lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * 8;
   for (long long r = wid; r < rows; r += nw) {
-    const float* s = S + r * L;
+    const float* s = S + r * Lp;
     float mx = -INFINITY;
     for (int i = lane; i < L; i += 32) mx = fmaxf(mx, s[i]);
 #pragma unroll
@@ -114,27 +115,27 @@ softmax_fwd_kernel(const float* __restrict__ S, long long rows, int L, __nv_bflo
     for (int i = lane; i < L; i += 32) sum += __expf(s[i] - mx);
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    __nv_bfloat16* p = P + r * L;
-    for (int i = lane; i < L; i += 32) p[i] = __float2bfloat16(__expf(s[i] - mx) * inv);
+    __nv_bfloat16* p = P + r * Lp;
+    for (int i = lane; i < Lp; i += 32) p[i] = __float2bfloat16(i < L ? __expf(s[i] - mx) * inv : 0.f);
   }
 }
 
-// dS = P * (dP - sum_k dP*P) * scale ; dP f32 -> dS bf16
+// dS = P * (dP - sum_k dP*P) * scale ; dP f32 -> dS bf16 (padded columns -> 0)
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dP,
-                   long long rows, int L, float scale, __nv_bfloat16* __restrict__ dS) {
+                   long long rows, int L, int Lp, float scale, __nv_bfloat16* __restrict__ dS) {
   const int lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * 8;
   for (long long r = wid; r < rows; r += nw) {
-    const __nv_bfloat16* p = P + r * L;
-    const float* d = dP + r * L;
+    const __nv_bfloat16* p = P + r * Lp;
+    const float* d = dP + r * Lp;
     float dot = 0.f;
     for (int i = lane; i < L; i += 32) dot += __bfloat162float(p[i]) * d[i];
     dot = warp_sum(dot);
-    __nv_bfloat16* o = dS + r * L;
-    for (int i = lane; i < L; i += 32)
-      o[i] = __float2bfloat16(__bfloat162float(p[i]) * (d[i] - dot) * scale);
+    __nv_bfloat16* o = dS + r * Lp;
+    for (int i = lane; i < Lp; i += 32)
+      o[i] = __float2bfloat16(i < L ? __bfloat162float(p[i]) * (d[i] - dot) * scale : 0.f);
   }
 }
 
@@ -171,23 +172,23 @@ int fdx_time_embed_bwd(const float* demb, const float* four, const float* h1, co
   return FDX_OK;
 }
 
-int fdx_softmax_fwd(const float* S, long long rows, int L, void* P_bf16, void* stream) {
-  FDX_REQUIRE(S && P_bf16 && rows > 0 && L > 0, "softmax_fwd: bad arguments");
+int fdx_softmax_fwd(const float* S, long long rows, int L, int Lp, void* P_bf16, void* stream) {
+  FDX_REQUIRE(S && P_bf16 && rows > 0 && L > 0 && Lp >= L, "softmax_fwd: bad arguments");
   long long grid = (rows + 7) / 8;
   if (grid > 148 * 16) grid = 148 * 16;
-  softmax_fwd_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(S, rows, L,
+  softmax_fwd_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(S, rows, L, Lp,
                                                                  (__nv_bfloat16*)P_bf16);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }
 
-int fdx_softmax_bwd(const void* P_bf16, const float* dP, long long rows, int L, float scale,
+int fdx_softmax_bwd(const void* P_bf16, const float* dP, long long rows, int L, int Lp, float scale,
                     void* dS_bf16, void* stream) {
-  FDX_REQUIRE(P_bf16 && dP && dS_bf16 && rows > 0 && L > 0, "softmax_bwd: bad arguments");
+  FDX_REQUIRE(P_bf16 && dP && dS_bf16 && rows > 0 && L > 0 && Lp >= L, "softmax_bwd: bad arguments");
   long long grid = (rows + 7) / 8;
   if (grid > 148 * 16) grid = 148 * 16;
   softmax_bwd_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)P_bf16, dP, rows, L, scale, (__nv_bfloat16*)dS_bf16);
+      (const __nv_bfloat16*)P_bf16, dP, rows, L, Lp, scale, (__nv_bfloat16*)dS_bf16);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

@@ -369,36 +369,41 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
 // ---------------------------------------------------------------------------
 // RMSNorm over channels, one warp per pixel.
 // ---------------------------------------------------------------------------
-template <int VPL>   // 16-byte vectors per lane: C = 256 * VPL
+constexpr int kRmsV = 4;   // up to 4 x 32 x 8 = 1024 channels, one warp per pixel
+
 __global__ void __launch_bounds__(256)
 rms_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long xps, long long npix, int C,
                const float* __restrict__ scale, float eps, __nv_bfloat16* __restrict__ y,
                long long yps) {
   const int lane = threadIdx.x & 31;
+  const int nv = C >> 3;
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * 8;
   for (long long p = wid; p < npix; p += nw) {
-    float f[VPL][8];
+    float f[kRmsV][8];
     float q = 0.f;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      load8(x + p * xps + (v * 32 + lane) * 8, f[v]);
+    for (int v = 0; v < kRmsV; ++v) {
+      if (v * 32 + lane < nv) {
+        load8(x + p * xps + (v * 32 + lane) * 8, f[v]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q += f[v][j] * f[v][j];
+        for (int j = 0; j < 8; ++j) q += f[v][j] * f[v][j];
+      }
     }
     q = warp_sum(q);
     const float r = rsqrtf(q / (float)C + eps);
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      float o[8];
+    for (int v = 0; v < kRmsV; ++v) {
+      if (v * 32 + lane < nv) {
+        float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = f[v][j] * r * scale[(v * 32 + lane) * 8 + j];
-      store8(y + p * yps + (v * 32 + lane) * 8, o);
+        for (int j = 0; j < 8; ++j) o[j] = f[v][j] * r * scale[(v * 32 + lane) * 8 + j];
+        store8(y + p * yps + (v * 32 + lane) * 8, o);
+      }
     }
   }
 }
 
-template <int VPL>
 __global__ void __launch_bounds__(256)
 rms_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                const __nv_bfloat16* __restrict__ dy, long long dps, long long npix, int C,
@@ -408,52 +413,61 @@ rms_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
   for (int i = threadIdx.x; i < C; i += 256) sh_ds[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const int nv = C >> 3;
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * 8;
-  float ds[VPL][8];
+  float ds[kRmsV][8];
 #pragma unroll
-  for (int v = 0; v < VPL; ++v)
+  for (int v = 0; v < kRmsV; ++v)
 #pragma unroll
     for (int j = 0; j < 8; ++j) ds[v][j] = 0.f;
   for (long long p = wid; p < npix; p += nw) {
-    float f[VPL][8], d[VPL][8];
+    float f[kRmsV][8], d[kRmsV][8];
     float q = 0.f;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      load8(x + p * xps + (v * 32 + lane) * 8, f[v]);
-      load8(dy + p * dps + (v * 32 + lane) * 8, d[v]);
+    for (int v = 0; v < kRmsV; ++v) {
+      if (v * 32 + lane < nv) {
+        load8(x + p * xps + (v * 32 + lane) * 8, f[v]);
+        load8(dy + p * dps + (v * 32 + lane) * 8, d[v]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q += f[v][j] * f[v][j];
+        for (int j = 0; j < 8; ++j) q += f[v][j] * f[v][j];
+      }
     }
     q = warp_sum(q);
     const float r = rsqrtf(q / (float)C + eps);
     float m = 0.f;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v)
+    for (int v = 0; v < kRmsV; ++v) {
+      if (v * 32 + lane < nv) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = f[v][j] * r;
-        ds[v][j] += d[v][j] * xh;
-        d[v][j] *= scale[(v * 32 + lane) * 8 + j];   // g = dy * scale
-        m += d[v][j] * xh;
+        for (int j = 0; j < 8; ++j) {
+          const float xh = f[v][j] * r;
+          ds[v][j] += d[v][j] * xh;
+          d[v][j] *= scale[(v * 32 + lane) * 8 + j];   // g = dy * scale
+          m += d[v][j] * xh;
+        }
       }
+    }
     m = warp_sum(m) / (float)C;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      float o[8];
-      if (accumulate) load8(dx + p * dxps + (v * 32 + lane) * 8, o);
+    for (int v = 0; v < kRmsV; ++v) {
+      if (v * 32 + lane < nv) {
+        float o[8];
+        if (accumulate) load8(dx + p * dxps + (v * 32 + lane) * 8, o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float val = r * (d[v][j] - f[v][j] * r * m);
-        o[j] = accumulate ? o[j] + val : val;
+        for (int j = 0; j < 8; ++j) {
+          const float val = r * (d[v][j] - f[v][j] * r * m);
+          o[j] = accumulate ? o[j] + val : val;
+        }
+        store8(dx + p * dxps + (v * 32 + lane) * 8, o);
       }
-      store8(dx + p * dxps + (v * 32 + lane) * 8, o);
     }
   }
 #pragma unroll
-  for (int v = 0; v < VPL; ++v)
+  for (int v = 0; v < kRmsV; ++v)
+    if (v * 32 + lane < nv)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sh_ds[(v * 32 + lane) * 8 + j], ds[v][j]);
+      for (int j = 0; j < 8; ++j) atomicAdd(&sh_ds[(v * 32 + lane) * 8 + j], ds[v][j]);
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += 256) atomicAdd(&dscale[i], sh_ds[i]);
 }
@@ -549,46 +563,28 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
 
 int fdx_rmsnorm_fwd(const fdx_act* x, const float* scale, float eps, const fdx_act* y,
                     void* stream) {
-  FDX_REQUIRE(x && x->ptr && y && y->ptr, "rmsnorm_fwd: null tensor");
-  FDX_REQUIRE(x->c % 256 == 0 && x->c <= 1024, "rmsnorm_fwd: C=%d must be 256/512/768/1024", x->c);
+  FDX_REQUIRE(x && x->ptr && y && y->ptr && scale, "rmsnorm_fwd: null tensor");
+  FDX_REQUIRE(x->c % 8 == 0 && x->c <= 1024, "rmsnorm_fwd: C=%d must be a multiple of 8, <= 1024", x->c);
   const long long npix = (long long)x->n * x->h * x->w;
   int grid = (int)((npix + 7) / 8);
   if (grid > 148 * 8) grid = 148 * 8;
-  cudaStream_t st = (cudaStream_t)stream;
-#define RMS_F(V)                                                                               \
-  rms_fwd_kernel<V><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pix_stride, npix,  \
-                                          x->c, scale, eps, (__nv_bfloat16*)y->ptr, y->pix_stride)
-  switch (x->c / 256) {
-    case 1: RMS_F(1); break;
-    case 2: RMS_F(2); break;
-    case 3: RMS_F(3); break;
-    default: RMS_F(4); break;
-  }
-#undef RMS_F
+  rms_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->ptr, x->pix_stride, npix,
+                                                         x->c, scale, eps, (__nv_bfloat16*)y->ptr,
+                                                         y->pix_stride);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }
 
 int fdx_rmsnorm_bwd(const fdx_act* x, const fdx_act* dy, const float* scale, float eps,
                     const fdx_act* dx, int accumulate, float* dscale, void* stream) {
-  FDX_REQUIRE(x && x->ptr && dy && dy->ptr && dx && dx->ptr, "rmsnorm_bwd: null tensor");
-  FDX_REQUIRE(x->c % 256 == 0 && x->c <= 1024, "rmsnorm_bwd: C=%d must be 256/512/768/1024", x->c);
+  FDX_REQUIRE(x && x->ptr && dy && dy->ptr && dx && dx->ptr && scale && dscale, "rmsnorm_bwd: null tensor");
+  FDX_REQUIRE(x->c % 8 == 0 && x->c <= 1024, "rmsnorm_bwd: C=%d must be a multiple of 8, <= 1024", x->c);
   const long long npix = (long long)x->n * x->h * x->w;
   int grid = (int)((npix + 7) / 8);
-  if (grid > 148 * 4) grid = 148 * 4;
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t shm = sizeof(float) * x->c;
-#define RMS_B(V)                                                                                 \
-  rms_bwd_kernel<V><<<grid, 256, shm, st>>>(                                                     \
-      (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, \
-      npix, x->c, scale, eps, (__nv_bfloat16*)dx->ptr, dx->pix_stride, accumulate, dscale)
-  switch (x->c / 256) {
-    case 1: RMS_B(1); break;
-    case 2: RMS_B(2); break;
-    case 3: RMS_B(3); break;
-    default: RMS_B(4); break;
-  }
-#undef RMS_B
+  if (grid > 148 * 2) grid = 148 * 2;
+  rms_bwd_kernel<<<grid, 256, sizeof(float) * x->c, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, npix, x->c,
+      scale, eps, (__nv_bfloat16*)dx->ptr, dx->pix_stride, accumulate, dscale);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

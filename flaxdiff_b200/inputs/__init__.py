@@ -37,7 +37,8 @@ class RandomEmbeddingEncoder(ConditioningEncoder):
 
     def _one(self, item) -> torch.Tensor:
         g = torch.Generator()
-        g.manual_seed((hash(str(item)) ^ self.seed) & 0x7FFFFFFF)
+        import zlib
+        g.manual_seed((zlib.crc32(str(item).encode()) ^ self.seed) & 0x7FFFFFFF)
         return torch.randn(self.seq_len, self.features, generator=g)
 
     def __call__(self, data) -> torch.Tensor:

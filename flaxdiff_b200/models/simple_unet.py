@@ -63,7 +63,8 @@ class Unet:
                  feature_depths: Sequence[int] = (64, 128, 256, 512),
                  attention_configs: Sequence[Optional[dict]] = ({"heads": 8},) * 4,
                  num_res_blocks: int = 2, num_middle_res_blocks: int = 1, activation="swish",
-                 norm_groups: int = 8, dtype=None, precision=None, named_norms: bool = False):
+                 norm_groups: int = 8, dtype=None, precision=None, named_norms: bool = False,
+                 context_dim: Optional[int] = None):
         self.output_channels = output_channels
         self.emb_features = emb_features
         self.feature_depths = tuple(feature_depths)
@@ -75,6 +76,9 @@ class Unet:
         self.dtype = dtype
         self.precision = precision
         self.named_norms = named_norms
+        # width of `textcontext` (e.g. 768 for CLIP): fixes the to_k / to_v kernel shapes exactly as flax
+        # infers them at `init` time.  None = self-attention (`textcontext=None`).
+        self.context_dim = context_dim
         if norm_groups <= 0:
             raise FdxError("Unet: norm_groups=0 (RMSNorm blocks) is not on the supported hot path")
         if output_channels != 3:
@@ -89,7 +93,7 @@ class Unet:
         self._n1 = "GroupNorm_0" if named_norms else "norm1"
         self._n2 = "GroupNorm_1" if named_norms else "norm2"
         self._nout = "GroupNorm_0" if named_norms else "conv_out_norm"
-        self._layout: Optional[ParamLayout] = None
+        self._layouts: Dict[Optional[int], ParamLayout] = {}
         self._freqs: Dict[str, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ structure
@@ -166,16 +170,17 @@ class Unet:
                 h = cout["heads"]
                 d = cin // h
                 base = f"{name}/Attention/Attention2"
+                cctx = self.context_dim if self.context_dim else cin
                 specs += [(f"{name}/RMSNorm_0/scale", (cin,)),
-                          (f"{base}/to_q/kernel", (cin, h, d)), (f"{base}/to_k/kernel", (cin, h, d)),
-                          (f"{base}/to_v/kernel", (cin, h, d)), (f"{base}/to_out_0/kernel", (h, d, cin))]
+                          (f"{base}/to_q/kernel", (cin, h, d)), (f"{base}/to_k/kernel", (cctx, h, d)),
+                          (f"{base}/to_v/kernel", (cctx, h, d)), (f"{base}/to_out_0/kernel", (h, d, cin))]
         specs += [(f"{self._nout}/scale", (self.feature_depths[0],)), (f"{self._nout}/bias", (self.feature_depths[0],))]
         return specs
 
     def layout(self) -> ParamLayout:
-        if self._layout is None:
-            self._layout = ParamLayout(self.param_specs())
-        return self._layout
+        if self.context_dim not in self._layouts:
+            self._layouts[self.context_dim] = ParamLayout(self.param_specs())
+        return self._layouts[self.context_dim]
 
     # ------------------------------------------------------------------ init
     def init(self, key, x=None, temb=None, textcontext=None, device=None) -> FlatParams:
@@ -183,6 +188,8 @@ class Unet:
         kernels (flax default kernel_init), zero biases, unit norm scales."""
         if device is None:
             device = x.device if isinstance(x, torch.Tensor) else torch.device("cuda")
+        if isinstance(textcontext, torch.Tensor):
+            self.context_dim = int(textcontext.shape[-1])      # flax infers kernel shapes from the inputs
         lay = self.layout()
         flat = torch.zeros(lay.total, dtype=F32, device=device)
         fp = FlatParams(lay, flat)
@@ -225,17 +232,33 @@ class Unet:
         if not x.is_cuda:
             raise FdxError("Unet.apply: CUDA tensors required (no CPU path in flaxdiff_b200)")
         fp = self._as_flat(params, x.device)
-        xin = x if x.dtype == BF16 else x.to(BF16)
-        out, _ = self.forward(fp, xin.contiguous(), temb, textcontext, save=False)
+        xin = (x if x.dtype == BF16 else x.to(BF16)).contiguous()
+        if x.dtype != BF16:                      # f32 -> bf16 through the libfdx cast (the flax module casts too)
+            pad = (-x.numel()) % 4
+            flat = x.to(F32).contiguous().reshape(-1)
+            if pad == 0:
+                xin = ops.cast_f32_bf16(flat).view(x.shape)
+        out, _ = self.forward(fp, xin, temb, textcontext, save=False)
         return out
 
     # ------------------------------------------------------------------ forward program
     def forward(self, fp: FlatParams, x_bf16: torch.Tensor, temb: torch.Tensor, textcontext=None,
                 save: bool = True):
         """Returns (F f32 [B,H,W,3], tape or None)."""
-        if textcontext is not None and any(c is not None for c in self.attention_configs):
-            raise FdxError("Unet: cross-attention to textcontext is not implemented yet; pass "
-                           "textcontext=None for self-attention")
+        has_attn = any(c is not None for c in self.attention_configs)
+        ctx16 = None
+        if textcontext is not None and has_attn:
+            if self.context_dim is None or int(textcontext.shape[-1]) != self.context_dim:
+                raise FdxError(f"Unet: textcontext width {tuple(textcontext.shape)} does not match the "
+                               f"parameters (context_dim={self.context_dim}); build / init the model with it")
+            tc = textcontext
+            if tc.shape[0] == 1 and x_bf16.shape[0] > 1:
+                tc = tc.expand(x_bf16.shape[0], -1, -1)
+            tc = tc.contiguous()
+            ctx16 = tc if tc.dtype == BF16 else ops.cast_f32_bf16(tc.to(F32))
+        elif textcontext is None and has_attn and self.context_dim is not None:
+            raise FdxError("Unet: parameters were built for cross-attention (context_dim set) but "
+                           "textcontext is None")
         W = fp.named
         W16 = fp.shadow()
         B, H, Wd, _ = x_bf16.shape
@@ -322,7 +345,7 @@ class Unet:
                 cur = dst
             elif kind == "attn":
                 dst = out_node(idx, h, w, cin)
-                rec = self._attn_fwd(name, cur, dst, cout["heads"], W, W16)
+                rec = self._attn_fwd(name, cur, dst, cout["heads"], W, W16, ctx16)
                 tape.append(rec)
                 cur = dst
             elif kind == "down":
@@ -377,31 +400,57 @@ class Unet:
         ops.conv3x3_fwd(a2, W16[f"{name}/conv2/conv/kernel"], W[f"{name}/conv2/conv/bias"], res=r, out=dst.t)
         return ("res", name, xin, dst, st1, a1, hmid, st2, a2)
 
-    def _attn_fwd(self, name, xin: Node, dst: Node, heads, W, W16):
+    @staticmethod
+    def _pad_heads(w: torch.Tensor, axis: int, d: int, dp: int) -> torch.Tensor:
+        """Zero-pad the head dimension d -> dp (tensor-core tiles need >= 32 columns per head)."""
+        if dp == d:
+            return w
+        pads = [0, 0] * (w.dim() - 1 - axis) + [0, dp - d]
+        return torch.nn.functional.pad(w, pads)
+
+    def _attn_fwd(self, name, xin: Node, dst: Node, heads, W, W16, ctx16=None):
         """TransformerBlock(only_pure_attention) (models/attention.py:321-380): xn = RMSNorm(x);
-        out = xn + to_out(softmax(q k^T / sqrt(d)) v), context = xn (self-attention)."""
+        out = xn + to_out(softmax(q k^T / sqrt(d)) v); keys/values come from `textcontext`
+        (cross-attention, e.g. 77 x 768) or from xn itself (self-attention).  Heads narrower than 32
+        and key counts that are not multiples of 32 are zero-padded for the tensor-core tiles."""
         x = xin.t
         Bn, hh, ww, C = x.shape
         L = hh * ww
         d = C // heads
+        dp = max(32, d)
+        HD = heads * dp
         base = f"{name}/Attention/Attention2"
+        dev = x.device
         xn = ops.rmsnorm_fwd(x, W[f"{name}/RMSNorm_0/scale"], ATTN_EPS)
         x2 = xn.view(Bn * L, C)
-        q = ops.linear_fwd(x2, W16[f"{base}/to_q/kernel"].view(C, C))
-        k = ops.linear_fwd(x2, W16[f"{base}/to_k/kernel"].view(C, C))
-        v = ops.linear_fwd(x2, W16[f"{base}/to_v/kernel"].view(C, C))
-        S = torch.empty((Bn, heads, L, L), dtype=F32, device=x.device)
-        ops.gemm(GEMM_KK, q, k, S, L, L, d, C, C, L, batch1=heads, batch2=Bn,
-                 a_s=(d, L * C), b_s=(d, L * C), d_s=(L * L, heads * L * L), alpha=d ** -0.5)
-        P = ops.softmax_fwd(S)
+        if ctx16 is None:
+            ctx, Lk, Cc = xn.view(Bn, L, C), L, C
+        else:
+            ctx, Lk, Cc = ctx16, ctx16.shape[1], ctx16.shape[2]
+        Lkp = (Lk + 31) // 32 * 32
+        wq = self._pad_heads(W16[f"{base}/to_q/kernel"], 2, d, dp).reshape(C, HD)
+        wk = self._pad_heads(W16[f"{base}/to_k/kernel"], 2, d, dp).reshape(Cc, HD)
+        wv = self._pad_heads(W16[f"{base}/to_v/kernel"], 2, d, dp).reshape(Cc, HD)
+        wo = self._pad_heads(W16[f"{base}/to_out_0/kernel"], 1, d, dp).reshape(HD, C)
+        q = ops.linear_fwd(x2, wq)                                        # [B*L, h*dp]
+        alloc = torch.zeros if Lkp != Lk else torch.empty
+        k = alloc((Bn, Lkp, HD), dtype=BF16, device=dev)
+        v = alloc((Bn, Lkp, HD), dtype=BF16, device=dev)
+        for w_, o_ in ((wk, k), (wv, v)):
+            ops.gemm(GEMM_KMN, ctx, w_, o_, Lk, HD, Cc, Cc, HD, HD, batch2=Bn,
+                     a_s=(0, Lk * Cc), d_s=(0, Lkp * HD))
+        S = torch.empty((Bn, heads, L, Lkp), dtype=F32, device=dev)
+        ops.gemm(GEMM_KK, q, k, S, L, Lkp, dp, HD, HD, Lkp, batch1=heads, batch2=Bn,
+                 a_s=(dp, L * HD), b_s=(dp, Lkp * HD), d_s=(L * Lkp, heads * L * Lkp), alpha=d ** -0.5)
+        P = ops.softmax_fwd(S, valid=Lk)
         del S
-        o = torch.empty((Bn * L, C), dtype=BF16, device=x.device)
-        ops.gemm(GEMM_KMN, P, v, o, L, d, L, L, C, C, batch1=heads, batch2=Bn,
-                 a_s=(L * L, heads * L * L), b_s=(d, L * C), d_s=(d, L * C))
+        o = torch.empty((Bn * L, HD), dtype=BF16, device=dev)
+        ops.gemm(GEMM_KMN, P, v, o, L, dp, Lkp, Lkp, HD, HD, batch1=heads, batch2=Bn,
+                 a_s=(L * Lkp, heads * L * Lkp), b_s=(dp, Lkp * HD), d_s=(dp, L * HD))
         out2 = dst.t
-        ops.gemm(GEMM_KMN, o, W16[f"{base}/to_out_0/kernel"].view(C, C), out2, Bn * L, C, C, C, C,
-                 out2.stride(2), res=xn, r_ld=C)
-        return ("attn", name, xin, dst, heads, xn, q, k, v, P, o)
+        ops.gemm(GEMM_KMN, o, wo, out2, Bn * L, C, HD, HD, C, out2.stride(2), res=xn, r_ld=C)
+        return ("attn", name, xin, dst, heads, xn, q, k, v, P, o, ctx if ctx16 is not None else None,
+                (wq, wk, wv, wo), Lk)
 
     # ------------------------------------------------------------------ backward program
     def backward(self, fp: FlatParams, saved: dict, dF: torch.Tensor, grads: FlatParams):
@@ -552,52 +601,74 @@ class Unet:
             ops.act_add(dx, dout, dx)
 
     def _attn_bwd(self, rec, W, W16, Gd, want, grad_of):
-        _, name, xin, dst, heads, xn, q, k, v, P, o = rec
+        _, name, xin, dst, heads, xn, q, k, v, P, o, ctx, (wq, wk, wv, wo), Lk = rec
         x = xin.t
         Bn, hh, ww, C = x.shape
         L = hh * ww
         d = C // heads
+        dp = max(32, d)
+        HD = heads * dp
+        Lkp = k.shape[1]
+        cross = ctx is not None
+        kv_src = ctx if cross else xn.view(Bn, L, C)
+        Cc = kv_src.shape[2]
         base = f"{name}/Attention/Attention2"
         dout = grad_of(dst)                      # [B,h,w,C] view
         M = Bn * L
         dev = x.device
         alpha = d ** -0.5
+
+        def grad_target(pname, shape_p):
+            """(buffer to accumulate into, finisher): padded heads go through a scratch buffer."""
+            g = Gd[pname]
+            if dp == d:
+                return g.view(shape_p), None
+            return torch.zeros(shape_p, dtype=F32, device=dev), g
+
+        def finish(tmp, g, axis_view, sl):
+            if g is not None:
+                g.add_(tmp.view(axis_view)[sl])
+
         # out = xn + o @ Wo
-        Wo16 = W16[f"{base}/to_out_0/kernel"].view(C, C)
-        ops.gemm(GEMM_MNMN, o, dout, Gd[f"{base}/to_out_0/kernel"], C, C, M, C, dout.stride(2), C,
-                 atomic=True, reduce_batch=True)
-        do = torch.empty((M, C), dtype=BF16, device=dev)
-        ops.gemm(GEMM_KK, dout, Wo16, do, M, C, C, dout.stride(2), C, C)
+        t_o, g_o = grad_target(f"{base}/to_out_0/kernel", (HD, C))
+        ops.gemm(GEMM_MNMN, o, dout, t_o, HD, C, M, HD, dout.stride(2), C, atomic=True, reduce_batch=True)
+        finish(t_o, g_o, (heads, dp, C), (slice(None), slice(0, d), slice(None)))
+        do = torch.empty((M, HD), dtype=BF16, device=dev)
+        ops.gemm(GEMM_KK, dout, wo, do, M, HD, C, dout.stride(2), C, HD)
         # o = P v
-        dv = torch.empty((M, C), dtype=BF16, device=dev)
-        ops.gemm(GEMM_MNMN, P, do, dv, L, d, L, L, C, C, batch1=heads, batch2=Bn,
-                 a_s=(L * L, heads * L * L), b_s=(d, L * C), d_s=(d, L * C))
-        dP = torch.empty((Bn, heads, L, L), dtype=F32, device=dev)
-        ops.gemm(GEMM_KK, do, v, dP, L, L, d, C, C, L, batch1=heads, batch2=Bn,
-                 a_s=(d, L * C), b_s=(d, L * C), d_s=(L * L, heads * L * L))
-        dS = ops.softmax_bwd(P, dP, alpha)
+        dv = torch.empty((Bn, Lkp, HD), dtype=BF16, device=dev)
+        ops.gemm(GEMM_MNMN, P, do, dv, Lkp, dp, L, Lkp, HD, HD, batch1=heads, batch2=Bn,
+                 a_s=(L * Lkp, heads * L * Lkp), b_s=(dp, L * HD), d_s=(dp, Lkp * HD))
+        dP = torch.empty((Bn, heads, L, Lkp), dtype=F32, device=dev)
+        ops.gemm(GEMM_KK, do, v, dP, L, Lkp, dp, HD, HD, Lkp, batch1=heads, batch2=Bn,
+                 a_s=(dp, L * HD), b_s=(dp, Lkp * HD), d_s=(L * Lkp, heads * L * Lkp))
+        dS = ops.softmax_bwd(P, dP, alpha, valid=Lk)
         del dP
-        dq = torch.empty((M, C), dtype=BF16, device=dev)
-        ops.gemm(GEMM_KMN, dS, k, dq, L, d, L, L, C, C, batch1=heads, batch2=Bn,
-                 a_s=(L * L, heads * L * L), b_s=(d, L * C), d_s=(d, L * C))
-        dk = torch.empty((M, C), dtype=BF16, device=dev)
-        ops.gemm(GEMM_MNMN, dS, q, dk, L, d, L, L, C, C, batch1=heads, batch2=Bn,
-                 a_s=(L * L, heads * L * L), b_s=(d, L * C), d_s=(d, L * C))
+        dq = torch.empty((M, HD), dtype=BF16, device=dev)
+        ops.gemm(GEMM_KMN, dS, k, dq, L, dp, Lkp, Lkp, HD, HD, batch1=heads, batch2=Bn,
+                 a_s=(L * Lkp, heads * L * Lkp), b_s=(dp, Lkp * HD), d_s=(dp, L * HD))
+        dk = torch.empty((Bn, Lkp, HD), dtype=BF16, device=dev)
+        ops.gemm(GEMM_MNMN, dS, q, dk, Lkp, dp, L, Lkp, HD, HD, batch1=heads, batch2=Bn,
+                 a_s=(L * Lkp, heads * L * Lkp), b_s=(dp, L * HD), d_s=(dp, Lkp * HD))
         del dS
-        # projections: y = xn @ Wx
+        # projection weight gradients: y = src @ W  ->  dW = src^T dy (reduced over tokens and images)
         x2 = xn.view(M, C)
+        t_q, g_q = grad_target(f"{base}/to_q/kernel", (C, HD))
+        ops.gemm(GEMM_MNMN, x2, dq, t_q, C, HD, M, C, HD, HD, atomic=True, reduce_batch=True)
+        finish(t_q, g_q, (C, heads, dp), (slice(None), slice(None), slice(0, d)))
+        for nm, dy_ in (("to_k", dk), ("to_v", dv)):
+            t_w, g_w = grad_target(f"{base}/{nm}/kernel", (Cc, HD))
+            ops.gemm(GEMM_MNMN, kv_src, dy_, t_w, Cc, HD, Lk, Cc, HD, HD, batch2=Bn,
+                     a_s=(0, Lk * Cc), b_s=(0, Lkp * HD), atomic=True, reduce_batch=True)
+            finish(t_w, g_w, (Cc, heads, dp), (slice(None), slice(None), slice(0, d)))
+        # d(xn) = dout (residual) + dq Wq^T (+ dk Wk^T + dv Wv^T for self-attention)
         dxn = torch.empty((Bn, hh, ww, C), dtype=BF16, device=dev)
         dxn2 = dxn.view(M, C)
-        first = True
-        for nm, dy in (("to_q", dq), ("to_k", dk), ("to_v", dv)):
-            ops.gemm(GEMM_MNMN, x2, dy, Gd[f"{base}/{nm}/kernel"], C, C, M, C, C, C, atomic=True,
-                     reduce_batch=True)
-            Wx = W16[f"{base}/{nm}/kernel"].view(C, C)
-            if first:
-                # dxn = dout (residual) + dy Wx^T
-                ops.gemm(GEMM_KK, dy, Wx, dxn2, M, C, C, C, C, C, res=dout, r_ld=dout.stride(2))
-                first = False
-            else:
-                ops.gemm(GEMM_KK, dy, Wx, dxn2, M, C, C, C, C, C, res=dxn2, r_ld=C)
+        ops.gemm(GEMM_KK, dq, wq, dxn2, M, C, HD, HD, HD, C, res=dout, r_ld=dout.stride(2))
+        if not cross:
+            for dy_, w_ in ((dk, wk), (dv, wv)):
+                # rows of the padded [B, Lkp, HD] buffers map to tokens batch by batch
+                ops.gemm(GEMM_KK, dy_, w_, dxn2, L, C, HD, HD, HD, C, batch2=Bn, a_s=(0, Lkp * HD),
+                         d_s=(0, L * C), res=dxn2, r_ld=C, r_s=(0, L * C))
         dx, acc = want(xin)
         ops.rmsnorm_bwd(x, dxn, W[f"{name}/RMSNorm_0/scale"], ATTN_EPS, dx, Gd[f"{name}/RMSNorm_0/scale"], acc)

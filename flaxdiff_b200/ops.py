@@ -392,17 +392,20 @@ def time_embed_bwd(demb, saved, W2, dW1, db1, dW2, db2):
                                     ptr(db2), stream_ptr()), "time_embed_bwd")
 
 
-def softmax_fwd(S: torch.Tensor) -> torch.Tensor:
-    L = S.shape[-1]
+def softmax_fwd(S: torch.Tensor, valid: Optional[int] = None) -> torch.Tensor:
+    """Row softmax over the first `valid` of the last dim's columns (rest are padding -> 0)."""
+    Lp = S.shape[-1]
+    L = Lp if valid is None else valid
     P = torch.empty(tuple(S.shape), dtype=torch.bfloat16, device=S.device)
-    check(load().fdx_softmax_fwd(ptr(S), ctypes.c_longlong(S.numel() // L), ctypes.c_int(L), ptr(P),
-                                 stream_ptr()), "softmax_fwd")
+    check(load().fdx_softmax_fwd(ptr(S), ctypes.c_longlong(S.numel() // Lp), ctypes.c_int(L), ctypes.c_int(Lp),
+                                 ptr(P), stream_ptr()), "softmax_fwd")
     return P
 
 
-def softmax_bwd(P: torch.Tensor, dP: torch.Tensor, scale: float) -> torch.Tensor:
-    L = P.shape[-1]
+def softmax_bwd(P: torch.Tensor, dP: torch.Tensor, scale: float, valid: Optional[int] = None) -> torch.Tensor:
+    Lp = P.shape[-1]
+    L = Lp if valid is None else valid
     dS = torch.empty(tuple(P.shape), dtype=torch.bfloat16, device=P.device)
-    check(load().fdx_softmax_bwd(ptr(P), ptr(dP), ctypes.c_longlong(P.numel() // L), ctypes.c_int(L),
-                                 ctypes.c_float(scale), ptr(dS), stream_ptr()), "softmax_bwd")
+    check(load().fdx_softmax_bwd(ptr(P), ptr(dP), ctypes.c_longlong(P.numel() // Lp), ctypes.c_int(L),
+                                 ctypes.c_int(Lp), ctypes.c_float(scale), ptr(dS), stream_ptr()), "softmax_bwd")
     return dS

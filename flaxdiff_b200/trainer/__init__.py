@@ -185,7 +185,10 @@ class GeneralDiffusionTrainer:
                         param_transforms=None, use_dynamic_scale=False):
         rngs, subkey = utils.split(rngs)
         if existing_state is None:
-            params = model.init(subkey, device=self.device)
+            ctx_ex = None
+            if self.input_config.conditions:
+                ctx_ex = self.input_config.conditions[0].get_unconditional()
+            params = model.init(subkey, textcontext=ctx_ex, device=self.device)
             ema = params.clone()
         else:
             params, ema = existing_state['params'], existing_state['ema_params']
@@ -193,7 +196,7 @@ class GeneralDiffusionTrainer:
         return state, state
 
     # ------------------------------------------------------------------ the step
-    def _fwd_bwd(self, images, noise, noise_level):
+    def _fwd_bwd(self, images, noise, noise_level, ctx=None):
         """noise-add -> UNet fwd -> loss -> UNet bwd; returns the loss tensor (f32[1])."""
         sched, tr, st = self.noise_schedule, self.model_output_transform, self.state
         B = images.shape[0]
@@ -205,7 +208,7 @@ class GeneralDiffusionTrainer:
         weight = sched.get_weights(noise_level, shape=(-1,)).to(torch.float32)
         _, t_model = sched.transform_inputs(None, noise_level)
         x_t, target, model_in = ops.diffuse_forward(images, noise, alpha, sigma, c_in, True, tr.target_kind)
-        F, saved = self.model.forward(st.params, model_in, t_model, None, save=True)
+        F, saved = self.model.forward(st.params, model_in, t_model, ctx, save=True)
         loss, dF = ops.loss_fwd_bwd(F, x_t, target, c_out, c_skip, weight, want_grad=True)
         self._grads.flat.zero_()
         self.model.backward(st.params, saved, dF, self._grads)
@@ -226,14 +229,21 @@ class GeneralDiffusionTrainer:
                 data = data.to(torch.float32)
             images = data.to(dev, non_blocking=True).contiguous()      # HOST -> DEVICE boundary
             B = images.shape[0]
-            local, _uncond_key = local.get_random_key()                 # CFG mask key (kept for key parity)
+            local, uncond_key = local.get_random_key()
+            ctx = None
+            if self.input_config.conditions:
+                # per-sample unconditional mask (bernoulli p = unconditional_prob) and null-embedding mixing
+                # (general_diffusion_trainer.py:266-275; inputs/__init__.py:123-146)
+                mask = utils.device_uniform(uncond_key, (B,), dev) < self.unconditional_prob
+                ctx = self.input_config.process_conditioning(batch, uncond_mask=mask)[0]
+                ctx = ctx.to(device=dev, dtype=torch.float32).contiguous()
             noise_level, local = self.noise_schedule.generate_timesteps(B, local)
             local, noise_key = local.get_random_key()
             noise = utils.device_normal(noise_key, tuple(images.shape), dev)
             if self.use_cuda_graph:
-                loss = self._graphed_fwd_bwd(images, noise, noise_level)
+                loss = self._graphed_fwd_bwd(images, noise, noise_level, ctx)
             else:
-                loss = self._fwd_bwd(images, noise, noise_level)
+                loss = self._fwd_bwd(images, noise, noise_level, ctx)
             gscale = 1.0
             if self.distributed_training and self.world_size > 1:
                 gscale = dp_allreduce_sum_(self._grads.flat, loss, self.world_size)
@@ -243,9 +253,11 @@ class GeneralDiffusionTrainer:
 
         return train_step
 
-    def _graphed_fwd_bwd(self, images, noise, noise_level):
+    def _graphed_fwd_bwd(self, images, noise, noise_level, ctx=None):
         if self._graph is None or self._static[0].shape != images.shape or self._static[0].dtype != images.dtype:
-            self._static = (images.clone(), noise.clone(), noise_level.clone())
+            self._static = [images.clone(), noise.clone(), noise_level.clone()]
+            if ctx is not None:
+                self._static.append(ctx.clone())
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -255,10 +267,11 @@ class GeneralDiffusionTrainer:
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._static_loss = self._fwd_bwd(*self._static)
-        s_img, s_noise, s_t = self._static
-        s_img.copy_(images, non_blocking=True)
-        s_noise.copy_(noise)
-        s_t.copy_(noise_level)
+        self._static[0].copy_(images, non_blocking=True)
+        self._static[1].copy_(noise)
+        self._static[2].copy_(noise_level)
+        if ctx is not None:
+            self._static[3].copy_(ctx)
         self._graph.replay()
         return self._static_loss.clone()
 

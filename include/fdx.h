@@ -88,7 +88,7 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
                       const float* gamma, const float* beta, float eps, int silu, float* ws,
                       float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
                       float* csum_img, float* csum_tot, void* stream);
-/* nn.RMSNorm(eps) over channels (models/attention.py:325-326). C in {256,512,768,1024}. */
+/* nn.RMSNorm(eps) over channels (models/attention.py:325-326). C a multiple of 8, <= 1024. */
 int fdx_rmsnorm_fwd(const fdx_act* x, const float* scale, float eps, const fdx_act* y,
                     void* stream);
 int fdx_rmsnorm_bwd(const fdx_act* x, const fdx_act* dy, const float* scale, float eps,
@@ -155,9 +155,10 @@ int fdx_time_embed_fwd(const float* t, const float* freqs, const float* W1, cons
 int fdx_time_embed_bwd(const float* demb, const float* four, const float* h1, const float* h2,
                        const float* W2, int B, int D, float* dh1_ws, float* dh2_ws, float* dW1,
                        float* db1, float* dW2, float* db2, void* stream);
-/* softmax of nn.dot_product_attention (models/attention.py:170-174): S f32 -> P bf16. */
-int fdx_softmax_fwd(const float* S, long long rows, int L, void* P_bf16, void* stream);
-int fdx_softmax_bwd(const void* P_bf16, const float* dP, long long rows, int L, float scale,
+/* softmax of nn.dot_product_attention (models/attention.py:170-174): S f32 -> P bf16.  Rows hold Lp
+ * columns of which the first L are real keys (cross-attention to 77 text tokens is padded to 96). */
+int fdx_softmax_fwd(const float* S, long long rows, int L, int Lp, void* P_bf16, void* stream);
+int fdx_softmax_bwd(const void* P_bf16, const float* dP, long long rows, int L, int Lp, float scale,
                     void* dS_bf16, void* stream);
 
 #ifdef __cplusplus

@@ -204,3 +204,77 @@ def test_train_step_vs_oracle(graph, monkeypatch):
     assert cos_n / (cos_a * cos_b) ** 0.5 > 0.9
     assert torch.isfinite(got).all()
     assert rel(trainer.state.params.shadow_flat_noupdate().float(), trainer.state.params.flat) < 4e-3
+
+
+@pytest.mark.parametrize("res,B,levels", [(32, 2, (None, {"heads": 8}, {"heads": 8}, {"heads": 8})),
+                                          (64, 1, (None, None, {"heads": 8}, {"heads": 8}))])
+def test_text_cross_attention_forward_backward_vs_oracle(res, B, levels):
+    """BASELINE config 4 structure: cross-attention to a (B, 77, 768) text context at several levels
+    (head widths 8..64, 77 keys padded to 96)."""
+    torch.manual_seed(0)
+    model = Unet(attention_configs=levels, dtype=torch.bfloat16, context_dim=768)
+    fp = model.init(4, device=dev)
+    x = torch.randn(B, res, res, 3, device=dev).bfloat16()
+    t = torch.randn(B, device=dev)
+    ctx = torch.randn(B, 77, 768, device=dev).bfloat16()
+    F, saved = model.forward(fp, x, t, ctx, save=True)
+    P = cpu_params(fp, True)
+    Fr = unet_ref.unet_forward(P, x.float().cpu(), t.cpu(), model._fourier_freqs(dev).cpu(), attention_configs=levels,
+                               textcontext=ctx.float().cpu())
+    assert rel(F, Fr) < 3e-2
+    dF = torch.randn(B, res, res, 3, device=dev) / (B * res * res * 3)
+    grads = fp.zeros_like()
+    model.backward(fp, saved, dF, grads)
+    (Fr * dF.cpu()).sum().backward()
+    num = den = 0.0
+    for k in P:
+        g, gr = grads.named[k].cpu(), P[k].grad
+        assert rel(g, gr) < 8e-2, k
+        num += (g - gr).pow(2).sum().item()
+        den += gr.pow(2).sum().item()
+    assert (num / den) ** 0.5 < 3e-2
+
+
+def test_cfg_euler_ancestral_sampling_vs_oracle(monkeypatch):
+    """Classifier-free guidance batching (samplers/common.py:70-96) with frozen random text embeddings."""
+    from flaxdiff_b200.inputs import ConditionalInputConfig, RandomEmbeddingEncoder
+    torch.manual_seed(0)
+    levels = (None, None, {"heads": 8}, {"heads": 8})
+    model = Unet(attention_configs=levels, dtype=torch.bfloat16, context_dim=768)
+    fp = model.init(4, device=dev)
+    enc = RandomEmbeddingEncoder(77, 768, device=dev)
+    cfg = DiffusionInputConfig("image", (32, 32, 3), [ConditionalInputConfig(enc)])
+    sched = KarrasVENoiseScheduler(1, sigma_max=80, rho=7, sigma_data=0.5).to(dev)
+    g = 3.0
+    smp = EulerAncestralSampler(model, sched, KarrasPredictionTransform(0.5), cfg, guidance_scale=g)
+    B, res, n = 2, 32, 3
+    prior = torch.randn(B, res, res, 3) * 80.0
+    noises = [torch.randn(B, res, res, 3) for _ in range(n)]
+    it = iter(noises)
+    monkeypatch.setattr(utils, "device_normal", lambda key, shape, device, dtype=torch.float32: next(it).to(device))
+    cond = enc(["a cat", "a dog"]).to(dev)
+    out = smp.generate_samples(fp, B, res, diffusion_steps=n, start_step=1000, priors=prior, device=dev,
+                               model_conditioning_inputs=(cond,))
+    # oracle: same loop with F = Fu + g (Fc - Fu)
+    P, freqs = cpu_params(fp), model._fourier_freqs(dev).cpu()
+    null = cfg.get_unconditionals()[0].cpu().expand(B, -1, -1)
+    steps = [float(s) for s in smp.get_steps(1000, 0, n)]
+    x = prior.clone()
+    for i, s in enumerate(steps):
+        cur, nxt = s / 1000.0, (steps[i + 1] if i + 1 < n else 0) / 1000.0
+        sig = R.karras_sigma(np.full(B, cur, np.float32))
+        s4 = torch.from_numpy(sig).view(-1, 1, 1, 1)
+        c_in, c_out, c_skip = (torch.from_numpy(a).view(-1, 1, 1, 1) for a in R.karras_coeffs(sig))
+        tm = torch.from_numpy(R.karras_model_time(sig))
+        with torch.no_grad():
+            Fc = unet_ref.unet_forward(P, x * c_in, tm, freqs, attention_configs=levels, textcontext=cond.float().cpu())
+            Fu = unet_ref.unet_forward(P, x * c_in, tm, freqs, attention_configs=levels, textcontext=null.float())
+        Fm = Fu + g * (Fc - Fu)
+        x0 = c_out * Fm + c_skip * x
+        if i == n - 1:
+            x = x0.clamp(-1, 1)
+            break
+        ns = R.karras_sigma(np.full(B, nxt, np.float32))
+        one = np.ones(B, np.float32)
+        x = torch.from_numpy(R.euler_ancestral_step(x.numpy(), x0.numpy(), noises[i].numpy(), one, sig, one, ns))
+    assert rel(out, x) < 6e-2
