@@ -23,12 +23,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FWD_GFLOP = {  # algorithmic forward GFLOP per image (BASELINE.md $2)
-    ("c2", 64): 18.17, ("c3", 256): 300.83, ("c5", 256): 300.83, ("c2_256", 256): 290.63,
+    ("c2", 64): 18.17, ("c3", 256): 300.83, ("c5", 256): 300.83, ("c4", 256): 298.03,
 }
 WORKLOADS = {
     # name: (resolution, per-GPU batch, attention configs, description)
     "c2": (64, 256, (None, None, None, None), "EDM UNet 64x64x3 bf16 B=256/GPU (BASELINE configs[1])"),
     "c3": (256, 64, (None, None, None, {"heads": 8}), "EDM UNet 256x256x3 self-attn bf16 B=64/GPU (configs[2])"),
+    # sampling-only workloads (python bench.py --workload c4|c5): value = denoise steps / s
+    "c4": (256, 64, (None, {"heads": 8}, {"heads": 8}, {"heads": 8}),
+           "text-cond UNet 256x256x3 (frozen random 77x768 text emb), CFG g=3, Euler-ancestral 30 steps, B=64 (configs[3])"),
+    "c5": (256, 32, (None, None, None, {"heads": 8}),
+           "EDM UNet 256x256x3 self-attn, Heun 18/50/100 steps, B=32/GPU (configs[4])"),
 }
 
 
@@ -195,6 +200,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.workload in ("c4", "c5"):
+        return run_sampling(args)
 
     import torch
     import torch.distributed as dist
@@ -353,6 +360,92 @@ def main():
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, model, res, acfg)
     print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_sampling(args):
+    """Sampling-only workloads: c4 (CFG Euler-ancestral, text cross-attention) and c5 (Heun sweep)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from flaxdiff_b200.inputs import ConditionalInputConfig, DiffusionInputConfig, RandomEmbeddingEncoder
+    from flaxdiff_b200.models.simple_unet import Unet
+    from flaxdiff_b200.predictors import KarrasPredictionTransform
+    from flaxdiff_b200.samplers import EulerAncestralSampler, HeunSampler
+    from flaxdiff_b200.schedulers import KarrasVENoiseScheduler
+    res, B, acfg, desc = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    hbm, tf_burst, tf_sust, src = load_peaks()
+    sched = KarrasVENoiseScheduler(1, sigma_max=80, rho=7, sigma_data=0.5).to(dev)
+    tr = KarrasPredictionTransform(0.5)
+    fwd = FWD_GFLOP[(args.workload, res)]
+    runs = []
+    if args.workload == "c4":
+        enc = RandomEmbeddingEncoder(77, 768, device=dev)
+        cfg = DiffusionInputConfig("image", (res, res, 3), [ConditionalInputConfig(enc)])
+        model = Unet(attention_configs=acfg, dtype=torch.bfloat16, context_dim=768)
+        params = model.init(4 + rank, device=dev)
+        smp = EulerAncestralSampler(model, sched, tr, cfg, guidance_scale=3.0)
+        cond = (enc([f"prompt {i}" for i in range(B)]).to(dev),)
+        plan = [(smp, 30, 2 * 30)]            # CFG doubles the model batch: 2 UNet evals per image-step
+    else:
+        cfg = DiffusionInputConfig("image", (res, res, 3), [])
+        model = Unet(attention_configs=acfg, dtype=torch.bfloat16)
+        params = model.init(4 + rank, device=dev)
+        smp = HeunSampler(model, sched, tr, cfg)
+        cond = ()
+        plan = [(smp, n, 2 * n - 1) for n in (18, 50, 100)]
+    clocks = ClockSampler(local_rank)
+    first = True
+    for smp_, n, nfe in plan:
+        smp_.generate_samples(params, B, res, diffusion_steps=min(n, 3), start_step=1000, device=dev,
+                              model_conditioning_inputs=cond)          # warm-up + graph capture
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if first:
+            clocks.start()
+            first = False
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        img = smp_.generate_samples(params, B, res, diffusion_steps=n, start_step=1000, device=dev,
+                                    model_conditioning_inputs=cond)
+        s1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms[0])
+        runs.append({"diffusion_steps": n, "unet_evals_per_image": nfe, "ms": ms,
+                     "denoise_steps_per_sec": n / (ms / 1e3), "image_steps_per_sec": world * B * n / (ms / 1e3),
+                     "unet_image_evals_per_sec": world * B * nfe / (ms / 1e3),
+                     "tensor_frac_of_sustained": (fwd * B * nfe / 1e3) / (ms / 1e3) / tf_sust,
+                     "finite": bool(torch.isfinite(img).all().item())})
+    clk = clocks.stop()
+    if rank == 0:
+        head = runs[0] if args.workload == "c4" else runs[1]
+        out = {"metric": "denoise_steps_per_sec", "value": head["denoise_steps_per_sec"], "unit": "steps/s",
+               "n_gpus": world, "steps": head["diffusion_steps"], "warmup": 3, "ms_per_step": head["ms"] / head["diffusion_steps"],
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": desc, "resolution": res, "batch_per_gpu": B, "parallelism": f"replicas{world}",
+                          "sampler": type(smp).__name__, "cuda_graph": True},
+               "runs": runs, "clocks": clk,
+               "roofline": {"bound": "tensor", "kernel": "UNet denoise evaluation (all libfdx launches of one step)",
+                            "achieved": head["tensor_frac_of_sustained"] * tf_sust, "peak": tf_sust, "unit": "TFLOP/s",
+                            "frac": head["tensor_frac_of_sustained"], "peak_source": f"{src} bf16_tflops_sustained",
+                            "traffic": None}}
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
