@@ -146,6 +146,53 @@ int fdx_conv3x3_dgrad(const fdx_act* dy, const void* w_hwio, const fdx_act* dx, 
   return FDX_OK;
 }
 
+int fdx_conv3x3_dgrad_gn(const fdx_act* dy, const void* w_hwio, const fdx_act* dz, const fdx_act* x,
+                         const float* ab, float* ws_slots, int slots, void* stream) {
+  int s;
+  if ((s = check_act(dy, "conv3x3_dgrad_gn dy")) != FDX_OK) return s;
+  if ((s = check_act(dz, "conv3x3_dgrad_gn dz")) != FDX_OK) return s;
+  if ((s = check_act(x, "conv3x3_dgrad_gn x")) != FDX_OK) return s;
+  FDX_REQUIRE(ab && ws_slots && slots > 0 && slots <= 64, "conv3x3_dgrad_gn: bad workspace");
+  FDX_REQUIRE(dz->c % 64 == 0 && dy->c % 64 == 0, "conv3x3_dgrad_gn: channels must be multiples of 64");
+  FDX_REQUIRE(dz->n == dy->n && dz->h == dy->h && dz->w == dy->w && x->n == dz->n && x->h == dz->h &&
+                  x->w == dz->w && x->c == dz->c,
+              "conv3x3_dgrad_gn: dims mismatch");
+  if ((long long)dz->h * dz->w < 128) {
+    fdx_set_error("conv3x3_dgrad_gn: fewer than 128 pixels per image");
+    return FDX_ERR_UNSUPPORTED;
+  }
+  const int cin = dz->c, cout = dy->c;
+  FDX_CUDA(cudaMemsetAsync(ws_slots, 0, sizeof(float) * 2 * (size_t)slots * dz->n * cin, (cudaStream_t)stream));
+  TcLaunch L{};
+  L.mode = TC_KK;
+  fill_act_operand(L.A, dy);
+  L.B.ptr = w_hwio;
+  L.B.dims[0] = cout; L.B.dims[1] = cin; L.B.dims[2] = 9; L.B.dims[3] = 1;
+  L.B.strides[0] = 1; L.B.strides[1] = cout; L.B.strides[2] = (uint64_t)cin * cout;
+  L.B.strides[3] = 9ull * cin * cout;
+  L.N = dz->n; L.W = dz->w; L.H = dz->h;
+  L.es = 1;
+  L.K = cout;
+  L.Ncols = cin;
+  L.alpha = 1.f;
+  L.ntaps = 9;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      const int t = ky * 3 + kx;
+      L.tap_dx[t] = kx - 1;
+      L.tap_dy[t] = ky - 1;
+      L.tap_b[t] = 8 - t;   // flipped tap
+    }
+  L.out = dz->ptr;
+  L.os_x = dz->pix_stride; L.os_y = dz->pix_stride * dz->w; L.os_n = dz->pix_stride * dz->w * dz->h;
+  L.res = x->ptr;
+  L.rs_x = x->pix_stride; L.rs_y = x->pix_stride * x->w; L.rs_n = x->pix_stride * x->w * x->h;
+  L.gn_ab = ab;
+  L.gn_ws = ws_slots;
+  L.gn_slots = slots;
+  return fdx_tc_launch(L, (cudaStream_t)stream);
+}
+
 int fdx_conv3x3_wgrad(const fdx_act* x, const fdx_act* dy, float* dw_hwio, int stride,
                       void* stream) {
   int s;

@@ -173,12 +173,15 @@ fdx_conv3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const long long obase = (long long)n * p.os_n + (long long)y * p.os_y + (long long)x * p.os_x;
       const long long rbase =
           p.res ? (long long)n * p.rs_n + (long long)y * p.rs_y + (long long)x * p.rs_x : 0;
-      mbar_wait(&tfull[acc], acc_ph);
-      tc_fence_after();
+      auto wait_acc = [&]() {
+        mbar_wait(&tfull[acc], acc_ph);
+        tc_fence_after();
+      };
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       {
-        EpiArgs ea{p.out, p.bias, p.rowvec, p.res, p.Ncols, 1.f};
-        epilogue_bf16_coalesced<BN>(ea, epi_stage + q * 4096, t_addr, lane, nt * BN, valid, obase, rbase, n);
+        EpiArgs ea{p.out, p.bias, p.rowvec, p.res, p.Ncols, 1.f, nullptr, nullptr, 0};
+        epilogue_bf16_coalesced<BN, false>(ea, epi_stage + q * 4096, t_addr, lane, nt * BN, valid, obase, rbase,
+                                           n, wait_acc);
       }
       tc_fence_before();
       __syncwarp();

@@ -248,6 +248,35 @@ im2col3_kernel(const void* __restrict__ src_, int sgn, int N, int H, int W, int 
   }
 }
 
+// ---- col2im for conv_out: the Cin->3 convolution is a (pixels x Cin)(Cin x 27) tensor-core GEMM whose
+//      f32 result col[p][t*3+k] = <x[p], w[t][:][k]> is scattered back here:
+//      y[p][k] = bias[k] + sum_t col[p + d(t)][t*3+k]   (taps outside the image contribute 0 = SAME padding)
+__global__ void __launch_bounds__(256)
+col2im3_kernel(const float* __restrict__ col, const float* __restrict__ bias, int N, int H, int W,
+               float* __restrict__ y) {
+  const long long npix = (long long)N * H * W;
+  const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f, b2 = bias ? bias[2] : 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(p % W);
+    const int py = (int)((p / W) % H);
+    float a0 = b0, a1 = b1, a2 = b2;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int sy = py + ky - 1;
+      if (sy < 0 || sy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int sx = px + kx - 1;
+        if (sx < 0 || sx >= W) continue;
+        const float* c = col + (p + (long long)(ky - 1) * W + (kx - 1)) * 32 + (ky * 3 + kx) * 3;
+        a0 += c[0]; a1 += c[1]; a2 += c[2];
+      }
+    }
+    y[p * 3 + 0] = a0; y[p * 3 + 1] = a1; y[p * 3 + 2] = a2;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -290,6 +319,17 @@ int fdx_conv_in_wgrad(const void* x_bf16, const fdx_act* dy, float* dw_hwio, flo
   FDX_REQUIRE(dy->c == 64, "conv_in_wgrad: Cout must be 64 (got %d)", dy->c);
   rank27_wgrad_kernel<false, +1><<<148 * 4, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy->ptr, dy->pix_stride, x_bf16, dy->n, dy->h, dy->w, dw_hwio, dbias);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_col2im3x3_c3(const float* col_f32, const float* bias, int N, int H, int W, float* y_f32,
+                     void* stream) {
+  FDX_REQUIRE(col_f32 && y_f32 && N > 0 && H > 0 && W > 0, "col2im3x3_c3: bad arguments");
+  const long long npix = (long long)N * H * W;
+  long long grid = (npix + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  col2im3_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(col_f32, bias, N, H, W, y_f32);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

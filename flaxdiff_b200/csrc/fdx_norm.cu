@@ -268,6 +268,41 @@ gn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ s
   }
 }
 
+// ab[n][0][c] = a = rstd*gamma_c ; ab[n][1][c] = b = beta_c - mean*a   (consumed by the fused dgrad epilogue)
+__global__ void __launch_bounds__(256)
+gn_coeffs_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int N, int HW, int C, int G, float eps,
+                 float* __restrict__ ab) {
+  const int cpg = C / G;
+  const float cnt = (float)HW * (float)cpg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)N * C;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / C), c = (int)(i % C), g = c / cpg;
+    const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
+    const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+    const float a = rsqrtf(var + eps) * gamma[c];
+    ab[((long long)n * 2) * C + c] = a;
+    ab[((long long)n * 2 + 1) * C + c] = beta[c] - mean * a;
+  }
+}
+
+// sums[n][c] = (S0, S1) <- sum over slots of wsl[slot][n][{0,1}][c]   (fused-epilogue workspace layout)
+__global__ void __launch_bounds__(256)
+gn_collapse_slots_kernel(const float* __restrict__ wsl, int slots, int N, int C, float* __restrict__ sums) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)N * C;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / C), c = (int)(i % C);
+    float s0 = 0.f, s1 = 0.f;
+    for (int sl = 0; sl < slots; ++sl) {
+      const float* b = wsl + (((long long)sl * N + n) * 2) * C + c;
+      s0 += b[0];
+      s1 += b[C];
+    }
+    sums[i * 2] = s0;
+    sums[i * 2 + 1] = s1;
+  }
+}
+
 // out[c] (+)= sum_r in[r][c]; 32 columns x 8 row lanes per block
 __global__ void __launch_bounds__(256)
 reduce_rows_kernel(const float* __restrict__ in, int R, int C, float* __restrict__ out, int accumulate) {
@@ -553,6 +588,55 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
       (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, HW, C,
       groups, stats, red, gamma, beta, eps, silu, (__nv_bfloat16*)dx->ptr, dx->pix_stride, accumulate,
       csum_img);
+  FDX_LAUNCH_CHECK();
+  if (csum_tot) {
+    reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(csum_img, N, C, csum_tot, 0);
+    FDX_LAUNCH_CHECK();
+  }
+  return FDX_OK;
+}
+
+int fdx_groupnorm_coeffs(const float* stats, const float* gamma, const float* beta, int N, int HW, int C,
+                         int groups, float eps, float* ab, void* stream) {
+  FDX_REQUIRE(stats && gamma && beta && ab && N > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0,
+              "groupnorm_coeffs: bad arguments");
+  long long grid = ((long long)N * C + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  gn_coeffs_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(stats, gamma, beta, N, HW, C, groups, eps, ab);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_groupnorm_bwd_dz(const fdx_act* x, const fdx_act* dz, int groups, const float* stats,
+                         const float* gamma, float eps, const float* ws_slots, int slots, float* ws,
+                         float* dgamma, float* dbeta, const fdx_act* dx, int accumulate, float* csum_img,
+                         float* csum_tot, void* stream) {
+  int s = gn_check(x, groups, "groupnorm_bwd_dz");
+  if (s != FDX_OK) return s;
+  FDX_REQUIRE(dz && dz->ptr && dx && dx->ptr && ws && ws_slots && slots > 0 && dgamma && dbeta,
+              "groupnorm_bwd_dz: null tensor");
+  FDX_REQUIRE(dz->c == x->c && dx->c == x->c && dz->n == x->n && dx->n == x->n && dz->h == x->h &&
+                  dz->w == x->w && dx->h == x->h && dx->w == x->w,
+              "groupnorm_bwd_dz: shape mismatch");
+  FDX_REQUIRE(!csum_tot || csum_img, "groupnorm_bwd_dz: csum_tot needs csum_img");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = x->n, C = x->c, HW = x->h * x->w;
+  float* sums = ws;                         // [N][C][2]
+  float* red = ws + 2LL * N * C;            // [N][G][2]
+  long long cg = ((long long)N * C + 255) / 256;
+  if (cg > 148 * 8) cg = 148 * 8;
+  gn_collapse_slots_kernel<<<(int)cg, 256, 0, st>>>(ws_slots, slots, N, C, sums);
+  FDX_LAUNCH_CHECK();
+  const int cb = (C + 31) / 32, gb = (N * groups + 7) / 8;
+  gn_bwd_finalize_kernel<<<cb + gb, 256, 0, st>>>(sums, stats, gamma, N, HW, C, groups, eps, cb, red, dgamma,
+                                                   dbeta);
+  FDX_LAUNCH_CHECK();
+  if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * N * C, st));
+  const size_t shm2 = csum_img ? sizeof(float) * (C + (kNT / (C / 8)) * C) : 0;
+  // dz already carries silu'(z): the second pass is the activation-free one (beta is not read)
+  gn_bwd_apply_kernel<<<gn_grid(x, 2), kNT, shm2, st>>>(
+      (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dz->ptr, dz->pix_stride, HW, C,
+      groups, stats, red, gamma, gamma, eps, 0, (__nv_bfloat16*)dx->ptr, dx->pix_stride, accumulate, csum_img);
   FDX_LAUNCH_CHECK();
   if (csum_tot) {
     reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(csum_img, N, C, csum_tot, 0);

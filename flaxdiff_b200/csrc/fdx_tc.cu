@@ -37,7 +37,8 @@ struct TcCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kSub * (kABytes + kBBytes);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
-                                    16384 /*epilogue staging: 4 warps x 4 KB*/;
+                                    16384 /*epilogue staging: 4 warps x 4 KB*/ +
+                                    4096 /*GroupNorm-backward column-sum exchange*/;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
@@ -69,6 +70,10 @@ struct TcDev {
   const float* rowvec;
   const void* res;
   long long rs_x, rs_y, rs_n;
+  // fused GroupNorm-backward first pass (GN kernels only; see fdx_epilogue.cuh)
+  const float* gn_ab;
+  float* gn_ws;
+  int gn_slots;
 };
 
 // TC_MNMN tile decode: tile -> (batch block bz, split, nt, mb, tap) and the K range [pb0, pb1)
@@ -92,7 +97,7 @@ __device__ __forceinline__ MnTile decode_mn(const TcDev& p, int tile) {
   return m;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool GN>
 __global__ void __launch_bounds__(kThreads, 1)
 fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
               const TcDev p) {
@@ -113,6 +118,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * S + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
   uint8_t* epi_stage = smem + S * Cfg::kStageBytes + 256;   // 16 KB, 128-byte aligned
+  float* epi_xchg = reinterpret_cast<float*>(epi_stage + 16384);   // 4 KB (GN only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -272,6 +278,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const int row = q * 32 + lane;       // accumulator row owned by this thread
     int acc = 0;
     uint32_t acc_phase = 0;
+    int gn_par = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       int nt;
       bool valid;
@@ -302,15 +309,19 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           obase += (long long)(mt_.bz % p.nyb) * p.os_y + (long long)(mt_.bz / p.nyb) * p.os_n;
         has_acc = (mt_.pb1 - mt_.pb0) > 0;
       }
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
+      auto wait_acc = [&]() {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+      };
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       if (!A_MN && !p.out_f32 && !p.out_atomic) {
-        // bf16 output: stage through shared memory so global stores / residual loads are coalesced
-        EpiArgs ea{p.out, p.bias, p.rowvec, p.res, p.Ncols, p.alpha};
-        epilogue_bf16_coalesced<BN>(ea, epi_stage + q * 4096, t_addr, lane, nt * BN, valid && has_acc, obase,
-                                    rbase, img);
-      } else
+        // bf16 output: stage through shared memory so global stores / side-input loads are coalesced
+        EpiArgs ea{p.out, p.bias, p.rowvec, p.res, p.Ncols, p.alpha, p.gn_ab, p.gn_ws, p.N};
+        epilogue_bf16_coalesced<BN, GN>(ea, epi_stage + q * 4096, t_addr, lane, nt * BN, valid && has_acc,
+                                        obase, rbase, img, wait_acc, q, epi_xchg, &gn_par,
+                                        GN ? tile % p.gn_slots : 0);
+      } else {
+      wait_acc();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -366,6 +377,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -381,31 +393,39 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   }
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool GN>
 int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    FDX_CUDA(cudaFuncSetAttribute(fdx_tc_kernel<BN, MODE>,
+    FDX_CUDA(cudaFuncSetAttribute(fdx_tc_kernel<BN, MODE, GN>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   int grid = fdx_num_sms();
   if (grid <= 0) return FDX_ERR_NO_DEVICE;
   if (d.ntiles < grid) grid = d.ntiles;
-  fdx_tc_kernel<BN, MODE><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA, mB, d);
+  fdx_tc_kernel<BN, MODE, GN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA, mB, d);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
+}
+
+template <int BN, int MODE>
+int launch_gn(const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d, cudaStream_t stream) {
+  if constexpr (MODE == TC_KK) {
+    if (d.gn_ab) return launch_cfg<BN, MODE, true>(mA, mB, d, stream);
+  }
+  return launch_cfg<BN, MODE, false>(mA, mB, d, stream);
 }
 
 template <int MODE>
 int launch_mode(int BN, const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d,
                 cudaStream_t stream) {
   switch (BN) {
-    case 64: return launch_cfg<64, MODE>(mA, mB, d, stream);
-    case 128: return launch_cfg<128, MODE>(mA, mB, d, stream);
-    case 192: return launch_cfg<192, MODE>(mA, mB, d, stream);
-    case 256: return launch_cfg<256, MODE>(mA, mB, d, stream);
+    case 64: return launch_gn<64, MODE>(mA, mB, d, stream);
+    case 128: return launch_gn<128, MODE>(mA, mB, d, stream);
+    case 192: return launch_gn<192, MODE>(mA, mB, d, stream);
+    case 256: return launch_gn<256, MODE>(mA, mB, d, stream);
   }
   fdx_set_error("tc: unsupported BN %d", BN);
   return FDX_ERR_UNSUPPORTED;
@@ -435,6 +455,12 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
   d.os_x = L.os_x; d.os_y = L.os_y; d.os_n = L.os_n; d.os_tap = L.os_tap; d.os_m = L.os_m;
   d.alpha = L.alpha; d.bias = L.bias; d.rowvec = L.rowvec; d.res = L.res;
   d.rs_x = L.rs_x; d.rs_y = L.rs_y; d.rs_n = L.rs_n;
+  d.gn_ab = L.gn_ab; d.gn_ws = L.gn_ws; d.gn_slots = L.gn_slots > 0 ? L.gn_slots : 1;
+  if (L.gn_ab) {
+    FDX_REQUIRE(L.mode == TC_KK && !L.gemm_like && L.res && L.gn_ws && !L.out_f32 && !L.out_atomic &&
+                    !L.bias && !L.rowvec,
+                "tc: GroupNorm-backward fusion needs a plain bf16 data-gradient launch");
+  }
 
   // ---- column tile --------------------------------------------------------
   // cost model per row tile: ntiles * (BN + 64)  (MMA columns incl. padding + A re-read per tile)
@@ -466,6 +492,10 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
     TN = 1;
   }
   d.TW = TW; d.TH = TH; d.TN = TN;
+  if (L.gn_ab && TN != 1) {
+    fdx_set_error("tc: GroupNorm-backward fusion needs at least 128 pixels per image (got %dx%d)", L.W, L.H);
+    return FDX_ERR_UNSUPPORTED;
+  }
   d.nxb = (L.W + TW - 1) / TW;
   d.nyb = (L.H + TH - 1) / TH;
   d.nnb = (L.N + TN - 1) / TN;
@@ -473,7 +503,7 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
 
   // halo-sharing variant: fewer TMA writes, but measured slower than the generic kernel on B200
   // (both are shared-memory-bandwidth bound); kept as an opt-in experiment.
-  if (L.mode != TC_MNMN && getenv("FDX_CONV3")) {
+  if (L.mode != TC_MNMN && !L.gn_ab && getenv("FDX_CONV3")) {
     const int r3 = fdx_conv3_launch(L, BN, stream);
     if (r3 != FDX_ERR_UNSUPPORTED) return r3;
   }

@@ -51,6 +51,11 @@ struct TcLaunch {
   const void* res;        // bf16 residual / accumulate source or null
   long long rs_x, rs_y, rs_n;
   int splits;             // TC_MNMN: split-K factor (0 = auto)
+  // Fused first pass of GroupNorm(+SiLU) backward (TC_KK only): res = the norm's input x,
+  // gn_ab = [N][2][Ncols] (a, b), gn_ws = [gn_slots][N][2][Ncols] zeroed sums; out receives dz.
+  const float* gn_ab;
+  float* gn_ws;
+  int gn_slots;
 };
 
 int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream);

@@ -562,17 +562,15 @@ class Unet:
         # conv2
         ops.conv3x3_wgrad(a2, dout, Gd[f"{name}/conv2/conv/kernel"])
         ops.colsum(dout, False, out=Gd[f"{name}/conv2/conv/bias"])
-        da2 = torch.empty_like(a2)
-        ops.conv3x3_dgrad(dout, W16[f"{name}/conv2/conv/kernel"], da2)
-        # norm2 + silu
-        dh = torch.empty_like(hmid)
-        # the same pass also emits the per-image / total column sums of dh: the timestep
+        # conv2 data gradient -> norm2 + silu backward (first pass fused into the dgrad epilogue).
+        # The same pass also emits the per-image / total column sums of dh: the timestep
         # row-vector gradient and the conv1 (= temb_projection) bias gradient
+        dh = torch.empty_like(hmid)
         drow = torch.empty((Bn, cout), dtype=F32, device=x.device)
-        ops.groupnorm_bwd(hmid, da2, G, st2, W[f"{name}/{self._n2}/scale"], W[f"{name}/{self._n2}/bias"], RES_EPS,
-                          True, Gd[f"{name}/{self._n2}/scale"], Gd[f"{name}/{self._n2}/bias"], dh, False,
-                          csum_img=drow, csum_tot=Gd[f"{name}/conv1/conv/bias"])
-        del da2
+        ops.conv_dgrad_groupnorm_bwd(dout, W16[f"{name}/conv2/conv/kernel"], hmid, G, st2,
+                                     W[f"{name}/{self._n2}/scale"], W[f"{name}/{self._n2}/bias"], RES_EPS,
+                                     Gd[f"{name}/{self._n2}/scale"], Gd[f"{name}/{self._n2}/bias"], dh, False,
+                                     csum_img=drow, csum_tot=Gd[f"{name}/conv1/conv/bias"])
         Gd[f"{name}/temb_projection/bias"].copy_(Gd[f"{name}/conv1/conv/bias"])
         drow16 = ops.cast_f32_bf16(drow)
         ops.gemm(GEMM_MNMN, emb16, drow16, Gd[f"{name}/temb_projection/kernel"], E, cout, Bn, E, cout, cout,
@@ -581,13 +579,12 @@ class Unet:
                  atomic=True)
         # conv1
         ops.conv3x3_wgrad(a1, dh, Gd[f"{name}/conv1/conv/kernel"])
-        da1 = torch.empty_like(a1)
-        ops.conv3x3_dgrad(dh, W16[f"{name}/conv1/conv/kernel"], da1)
-        del dh
-        # norm1 + silu -> dx
+        # conv1 data gradient -> norm1 + silu backward -> dx
         dx, acc = want(xin)
-        ops.groupnorm_bwd(x, da1, G, st1, W[f"{name}/{self._n1}/scale"], W[f"{name}/{self._n1}/bias"], RES_EPS, True,
-                          Gd[f"{name}/{self._n1}/scale"], Gd[f"{name}/{self._n1}/bias"], dx, acc)
+        ops.conv_dgrad_groupnorm_bwd(dh, W16[f"{name}/conv1/conv/kernel"], x, G, st1,
+                                     W[f"{name}/{self._n1}/scale"], W[f"{name}/{self._n1}/bias"], RES_EPS,
+                                     Gd[f"{name}/{self._n1}/scale"], Gd[f"{name}/{self._n1}/bias"], dx, acc)
+        del dh
         # residual path
         if cin != cout:
             kn = f"{name}/residual_conv/conv/"

@@ -7,6 +7,7 @@ Python: each wrapper marshals pointers, shapes and the current CUDA stream.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -121,6 +122,65 @@ def groupnorm_bwd(x, dy, groups, stats, gamma, beta, eps, silu, dgamma, dbeta, d
                                    stream_ptr()),
           "groupnorm_bwd")
     return dx
+
+
+GN_FUSE_SLOTS = 8
+GN_FUSE_MIN_PIXELS = 128    # fdx_conv3x3_dgrad_gn needs one image per 128-pixel tile
+
+
+def groupnorm_coeffs(stats, gamma, beta, hw: int, eps: float) -> torch.Tensor:
+    """ab[n][0][c] = rstd*gamma_c, ab[n][1][c] = beta_c - mean*rstd*gamma_c (f32)."""
+    n, groups = stats.shape[0], stats.shape[1]
+    c = gamma.numel()
+    ab = torch.empty((n, 2, c), dtype=torch.float32, device=stats.device)
+    check(load().fdx_groupnorm_coeffs(ptr(stats), ptr(gamma), ptr(beta), ctypes.c_int(n), ctypes.c_int(hw),
+                                      ctypes.c_int(c), ctypes.c_int(groups), ctypes.c_float(eps), ptr(ab),
+                                      stream_ptr()), "groupnorm_coeffs")
+    return ab
+
+
+def conv3x3_dgrad_gn(dy: torch.Tensor, w_hwio: torch.Tensor, dz: torch.Tensor, x: torch.Tensor,
+                     ab: torch.Tensor, slots: int = GN_FUSE_SLOTS) -> torch.Tensor:
+    """Stride-1 data gradient with the first pass of GroupNorm(+SiLU) backward fused into its epilogue:
+    writes dz = dgrad * silu'(a x + b) and returns the per-slot sums workspace for groupnorm_bwd_dz."""
+    n, c = dz.shape[0], dz.shape[-1]
+    ws = torch.empty((slots, n, 2, c), dtype=torch.float32, device=dz.device)
+    check(load().fdx_conv3x3_dgrad_gn(ctypes.byref(act(dy, "dy")), ptr(w_hwio), ctypes.byref(act(dz, "dz")),
+                                      ctypes.byref(act(x, "x")), ptr(ab), ptr(ws), ctypes.c_int(slots),
+                                      stream_ptr()), "conv3x3_dgrad_gn")
+    return ws
+
+
+def groupnorm_bwd_dz(x, dz, groups, stats, gamma, eps, ws_slots, dgamma, dbeta, dx,
+                     accumulate: bool = False, csum_img=None, csum_tot=None) -> torch.Tensor:
+    red = torch.empty(2 * x.shape[0] * (x.shape[-1] + groups), dtype=torch.float32, device=x.device)
+    check(load().fdx_groupnorm_bwd_dz(ctypes.byref(act(x, "x")), ctypes.byref(act(dz, "dz")),
+                                      ctypes.c_int(groups), ptr(stats), ptr(gamma), ctypes.c_float(eps),
+                                      ptr(ws_slots), ctypes.c_int(ws_slots.shape[0]), ptr(red), ptr(dgamma),
+                                      ptr(dbeta), ctypes.byref(act(dx, "dx")),
+                                      ctypes.c_int(1 if accumulate else 0), ptr(csum_img), ptr(csum_tot),
+                                      stream_ptr()), "groupnorm_bwd_dz")
+    return dx
+
+
+def conv_dgrad_groupnorm_bwd(dy, w_hwio, x, groups, stats, gamma, beta, eps, dgamma, dbeta, dx,
+                             accumulate: bool = False, csum_img=None, csum_tot=None,
+                             fused: Optional[bool] = None) -> torch.Tensor:
+    """d/dx of conv3x3(silu(groupnorm(x))) given dy = d/d(conv output): data gradient, then the two-pass
+    GroupNorm backward.  FDX_GN_FUSE=1 selects the fused dgrad epilogue instead (parity-tested, but
+    measured slower on B200 except when Cout >= 2 Cin: one epilogue warp per scheduler cannot hide the
+    latency of the silu' arithmetic - profiles/layers_r01_gn_fusion.txt)."""
+    da = torch.empty(tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    if fused is None:
+        fused = bool(os.environ.get("FDX_GN_FUSE"))
+    if fused and x.shape[1] * x.shape[2] >= GN_FUSE_MIN_PIXELS:
+        ab = groupnorm_coeffs(stats, gamma, beta, x.shape[1] * x.shape[2], eps)
+        ws = conv3x3_dgrad_gn(dy, w_hwio, da, x, ab)
+        return groupnorm_bwd_dz(x, da, groups, stats, gamma, eps, ws, dgamma, dbeta, dx, accumulate,
+                                csum_img=csum_img, csum_tot=csum_tot)
+    conv3x3_dgrad(dy, w_hwio, da)
+    return groupnorm_bwd(x, da, groups, stats, gamma, beta, eps, True, dgamma, dbeta, dx, accumulate,
+                         csum_img=csum_img, csum_tot=csum_tot)
 
 
 def rmsnorm_fwd(x, scale, eps: float, out=None) -> torch.Tensor:
@@ -319,6 +379,21 @@ def conv_in_wgrad_direct(x_bf16, dy, dw, dbias):
 
 
 def conv_out_fwd(x: torch.Tensor, w: torch.Tensor, bias) -> torch.Tensor:
+    """conv_out Cin->3: one tcgen05 GEMM (pixels x Cin)(Cin x 27, padded to 32) with f32 output, then the
+    col2im scatter that adds the nine taps' partial sums and the bias."""
+    n, h, w_, cin = x.shape
+    wr = torch.zeros((cin, 32), dtype=torch.float32, device=x.device)
+    wr[:, :27] = w.reshape(9, cin, 3).permute(1, 0, 2).reshape(cin, 27)       # [ci][(t,k)]
+    col = torch.empty((n * h * w_, 32), dtype=torch.float32, device=x.device)
+    gemm(GEMM_KMN, x, cast_f32_bf16(wr), col, n * h * w_, 32, cin, x.stride(2), 32, 32)
+    y = torch.empty((n, h, w_, 3), dtype=torch.float32, device=x.device)
+    check(load().fdx_col2im3x3_c3(ptr(col), ptr(bias), ctypes.c_int(n), ctypes.c_int(h), ctypes.c_int(w_),
+                                  ptr(y), stream_ptr()), "col2im3x3_c3")
+    return y
+
+
+def conv_out_fwd_direct(x: torch.Tensor, w: torch.Tensor, bias) -> torch.Tensor:
+    """Workspace-free CUDA-core variant (fdx_conv_out_fwd)."""
     n, h, w_, c = x.shape
     y = torch.empty((n, h, w_, 3), dtype=torch.float32, device=x.device)
     check(load().fdx_conv_out_fwd(ctypes.byref(act(x, "x")), ptr(w), ptr(bias), ptr(y), stream_ptr()),

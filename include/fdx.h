@@ -88,6 +88,22 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
                       const float* gamma, const float* beta, float eps, int silu, float* ws,
                       float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
                       float* csum_img, float* csum_tot, void* stream);
+/* Fused variant of the backward above: the data-gradient convolution that PRODUCES dy applies
+ * silu'(z) in its epilogue and accumulates the first-pass sums, so x and dy are read once less.
+ *   fdx_groupnorm_coeffs : ab[n][0][c] = rstd*gamma_c, ab[n][1][c] = beta_c - mean*rstd*gamma_c
+ *   fdx_conv3x3_dgrad_gn : stride-1 3x3 data gradient (as fdx_conv3x3_dgrad) writing
+ *                          dz = dgrad * silu'(a x + b) and ws_slots[slot][n][{0,1}][c] += (sum dz, sum dz*x);
+ *                          zeroes ws_slots (slots*N*2*C floats) itself; FDX_ERR_UNSUPPORTED when an image
+ *                          has fewer than 128 pixels (caller then uses the two-pass path)
+ *   fdx_groupnorm_bwd_dz : second pass from dz; ws as in fdx_groupnorm_bwd. */
+int fdx_groupnorm_coeffs(const float* stats, const float* gamma, const float* beta, int N, int HW, int C,
+                         int groups, float eps, float* ab, void* stream);
+int fdx_conv3x3_dgrad_gn(const fdx_act* dy, const void* w_hwio, const fdx_act* dz, const fdx_act* x,
+                         const float* ab, float* ws_slots, int slots, void* stream);
+int fdx_groupnorm_bwd_dz(const fdx_act* x, const fdx_act* dz, int groups, const float* stats,
+                         const float* gamma, float eps, const float* ws_slots, int slots, float* ws,
+                         float* dgamma, float* dbeta, const fdx_act* dx, int accumulate, float* csum_img,
+                         float* csum_tot, void* stream);
 /* nn.RMSNorm(eps) over channels (models/attention.py:325-326). C a multiple of 8, <= 1024. */
 int fdx_rmsnorm_fwd(const fdx_act* x, const float* scale, float eps, const fdx_act* y,
                     void* stream);
@@ -140,6 +156,10 @@ int fdx_conv_in_wgrad(const void* x_bf16, const fdx_act* dy, float* dw_hwio, flo
  * ones_col (bias row).  dW_in = col^T dY ; dW_out = x^T col (via fdx_gemm MNMN). */
 int fdx_im2col3x3_c3(const void* src, int src_is_f32, int sgn, int N, int H, int W, int ones_col,
                      void* col_bf16, void* stream);
+/* Scatter step of the tensor-core conv_out (models/simple_unet.py:212-221): col f32 [N*H*W][32] holds
+ * <x[p], w[t][:][k]> at column t*3+k; y[p][k] = bias[k] + sum_t col[p + d(t)][t*3+k], SAME padding. */
+int fdx_col2im3x3_c3(const float* col_f32, const float* bias, int N, int H, int W, float* y_f32,
+                     void* stream);
 /* conv_out Cin->3 (models/simple_unet.py:212-221): y f32 [N,H,W,3] dense. */
 int fdx_conv_out_fwd(const fdx_act* x, const float* w_hwio, const float* bias, float* y_f32,
                      void* stream);

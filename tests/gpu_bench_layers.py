@@ -34,7 +34,39 @@ def timeit(fn, iters=10):
     return s.elapsed_time(e) / iters
 
 
+def gn_fusion(res, B):
+    """dgrad + two-pass GroupNorm backward against the fused dgrad epilogue, per layer shape."""
+    print(f"GN-backward fusion, res={res} B={B}: ms for [dgrad | gn_bwd 2-pass] vs [dgrad_gn | gn_bwd_dz]", flush=True)
+    t = [0.0, 0.0, 0.0, 0.0]
+    for div, cin, cout, stride in SHAPES:
+        ho = res // div
+        if stride != 1 or ho * ho < 128:
+            continue
+        x = (torch.randn(B, ho, ho, cin, device=dev) * 1.5 + 0.3).bfloat16()
+        w = (torch.randn(3, 3, cin, cout, device=dev) / (3 * cin ** 0.5)).bfloat16()
+        dy = torch.randn(B, ho, ho, cout, device=dev).bfloat16()
+        da = torch.empty_like(x)
+        dx = torch.empty_like(x)
+        g, b = torch.ones(cin, device=dev), torch.zeros(cin, device=dev)
+        dg, db = torch.zeros(cin, device=dev), torch.zeros(cin, device=dev)
+        st = ops.groupnorm_stats(x, 8)
+        ab = ops.groupnorm_coeffs(st, g, b, ho * ho, 1e-4)
+        ws = ops.conv3x3_dgrad_gn(dy, w, da, x, ab)
+        m0 = timeit(lambda: ops.conv3x3_dgrad(dy, w, da))
+        m1 = timeit(lambda: ops.groupnorm_bwd(x, da, 8, st, g, b, 1e-4, True, dg, db, dx))
+        m2 = timeit(lambda: (ops.groupnorm_coeffs(st, g, b, ho * ho, 1e-4), ops.conv3x3_dgrad_gn(dy, w, da, x, ab)))
+        m3 = timeit(lambda: ops.groupnorm_bwd_dz(x, da, 8, st, g, 1e-4, ws, dg, db, dx))
+        for i, m in enumerate((m0, m1, m2, m3)):
+            t[i] += m
+        print(f"{ho:4d}x{ho:<4d} {cin:4d}<-{cout:<4d} | {m0:7.3f} {m1:7.3f} = {m0+m1:7.3f} | {m2:7.3f} {m3:7.3f} = {m2+m3:7.3f}",
+              flush=True)
+        del x, w, dy, da, dx
+    print(f"TOTAL | {t[0]:7.3f} {t[1]:7.3f} = {t[0]+t[1]:7.3f} | {t[2]:7.3f} {t[3]:7.3f} = {t[2]+t[3]:7.3f}", flush=True)
+
+
 def main():
+    if len(sys.argv) > 3 and sys.argv[3] == "gn":
+        return gn_fusion(int(sys.argv[1]), int(sys.argv[2]))
     res = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     B = int(sys.argv[2]) if len(sys.argv) > 2 else (256 if res == 64 else 64)
     only = sys.argv[3] if len(sys.argv) > 3 else None
