@@ -67,6 +67,20 @@ def load_peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def roofline_traffic(workload: str, batch: int) -> dict:
+    """DRAM bytes the tensor-core engine moved in one step, from the committed ncu pass (profiles/) of the
+    same workload; null when no capture exists for this workload / batch."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "roofline_traffic.json")) as f:
+            rec = json.load(f).get(workload)
+        if rec and rec.get("batch_per_gpu") == batch:
+            return {"traffic": rec["dram_bytes_per_step"], "traffic_unit": "bytes per step (all tc launches)",
+                    "traffic_source": rec["source"]}
+    except Exception:  # noqa: BLE001
+        pass
+    return {"traffic": None}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -358,7 +372,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "fdx_tc_kernel (tcgen05 tap-GEMM; all conv/GEMM launches of one step)",
                      "achieved": tc_tflops, "peak": tf_sust, "unit": "TFLOP/s", "frac": tc_tflops / tf_sust,
                      "peak_source": f"{src} bf16_tflops_sustained", "launches": tc_calls, "ms_in_step": tc_ms,
-                     "share_of_step": tc_ms / ms_dev, "traffic": None},
+                     "share_of_step": tc_ms / ms_dev, **roofline_traffic(args.workload, B)},
         "clocks": clk,
         "sample": sample,
     }

@@ -34,7 +34,7 @@ struct C3Cfg {
 struct C3Dev {
   int nxb, nyb, nimg, W, H;
   int kchunks, K, Ncols, nblks, ntiles;
-  int tap_b[9];
+  int tap_b[kTcMaxTaps];
   void* out;
   long long os_x, os_y, os_n;
   const float* bias;

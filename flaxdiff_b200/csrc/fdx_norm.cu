@@ -238,26 +238,30 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
 }
 
 // finalize: blocks [0, cb) reduce over images -> dgamma / dbeta (accumulated into the gradient
-// buffers), 32 channels x 8 image lanes per block; blocks [cb, cb + gb) reduce over the channels of
-// a group -> red[n][g], one warp per (image, group).
+// buffers), 8 channels x 32 image lanes per block (the image loop is a chain of dependent-latency
+// loads: 32 lanes x 4-way unrolling keeps it to one or two round trips); blocks [cb, cb + gb) reduce
+// over the channels of a group -> red[n][g], one warp per (image, group).
+constexpr int kFinC = 8;     // channels per dgamma/dbeta block
 __global__ void __launch_bounds__(256)
 gn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ stats,
                        const float* __restrict__ gamma, int N, int HW, int C, int G, float eps, int cb,
                        float* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int cpg = C / G;
   const float cnt = (float)HW * (float)cpg;
-  __shared__ float sh0[8][33], sh1[8][33];
+  __shared__ float sh0[32][kFinC + 1], sh1[32][kFinC + 1];
   if ((int)blockIdx.x < cb) {
-    const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
+    const int cl = threadIdx.x % kFinC, nl = threadIdx.x / kFinC;
+    const int c = blockIdx.x * kFinC + cl;
     float a0 = 0.f, a1 = 0.f;
     if (c < C) {
       const int g = c / cpg;
-      for (int n = nl; n < N; n += 8) {
-        const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
-        const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
-        const float rstd = rsqrtf(var + eps);
+#pragma unroll 4
+      for (int n = nl; n < N; n += 32) {
+        const float2 st = *reinterpret_cast<const float2*>(stats + (long long)n * 2 * G + 2 * g);
         const float2 s = *reinterpret_cast<const float2*>(ws + ((long long)n * C + c) * 2);
+        const float mean = st.x / cnt;
+        const float var = fmaxf(0.f, st.y / cnt - mean * mean);
+        const float rstd = rsqrtf(var + eps);
         a0 += s.x;
         a1 += rstd * (s.y - mean * s.x);
       }
@@ -268,7 +272,7 @@ gn_bwd_finalize_kernel(const float* __restrict__ ws, const float* __restrict__ s
     if (nl == 0 && c < C) {
       float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { t0 += sh0[k][cl]; t1 += sh1[k][cl]; }
+      for (int k = 0; k < 32; ++k) { t0 += sh0[k][cl]; t1 += sh1[k][cl]; }
       dbeta[c] += t0;
       dgamma[c] += t1;
     }
@@ -659,7 +663,7 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
         (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, HW, C,
         groups, stats, gamma, beta, eps, sums);
   FDX_LAUNCH_CHECK();
-  const int cb = (C + 31) / 32, gb = (N * groups + 7) / 8;
+  const int cb = (C + kFinC - 1) / kFinC, gb = (N * groups + 7) / 8;
   gn_bwd_finalize_kernel<<<cb + gb, 256, 0, st>>>(sums, stats, gamma, N, HW, C, groups, eps, cb, red, dgamma,
                                                    dbeta);
   FDX_LAUNCH_CHECK();
@@ -704,7 +708,7 @@ int fdx_groupnorm_bwd_dz(const fdx_act* x, const fdx_act* dz, int groups, const 
   if (cg > 148 * 8) cg = 148 * 8;
   gn_collapse_slots_kernel<<<(int)cg, 256, 0, st>>>(ws_slots, slots, N, C, sums);
   FDX_LAUNCH_CHECK();
-  const int cb = (C + 31) / 32, gb = (N * groups + 7) / 8;
+  const int cb = (C + kFinC - 1) / kFinC, gb = (N * groups + 7) / 8;
   gn_bwd_finalize_kernel<<<cb + gb, 256, 0, st>>>(sums, stats, gamma, N, HW, C, groups, eps, cb, red, dgamma,
                                                    dbeta);
   FDX_LAUNCH_CHECK();

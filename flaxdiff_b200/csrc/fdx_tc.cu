@@ -49,7 +49,8 @@ struct TcDev {
   int W, H, N;
   int es;
   int ntaps;
-  int tap_dx[9], tap_dy[9], tap_b[9];
+  int tap_dx[kTcMaxTaps], tap_dy[kTcMaxTaps], tap_b[kTcMaxTaps];
+  int es_b, tap_bdx[kTcMaxTaps], tap_bdy[kTcMaxTaps];   // TC_MNMN strided / shifted B view
   int kchunks;           // K chunks per tap (TC_KK/TC_KMN)
   int K;
   int M;                 // TC_MNMN valid rows
@@ -214,10 +215,11 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
               tma_load_4d(sa + j * (kBK * 128), &mapA, &full[stage], ch,
                           xb * p.TW * p.es + p.tap_dx[tt], yb * p.TH * p.es + p.tap_dy[tt], nb * p.TN);
             }
+            const int tb = (p.tpp == 2) ? 0 : t;    // per-tap B views only without tap pairing
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(sb + j * (kBK * 128), &mapB, &full[stage], nt * BN + j * 64, xb * p.TW,
-                          yb * p.TH, nb * p.TN);
+              tma_load_4d(sb + j * (kBK * 128), &mapB, &full[stage], nt * BN + j * 64,
+                          xb * p.TW * p.es_b + p.tap_bdx[tb], yb * p.TH * p.es_b + p.tap_bdy[tb], nb * p.TN);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
@@ -441,7 +443,7 @@ int pow2_floor(int v) {
 
 int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
   FDX_REQUIRE(L.mode >= TC_KK && L.mode <= TC_MNMN, "tc: bad mode %d", L.mode);
-  FDX_REQUIRE(L.ntaps >= 1 && L.ntaps <= 9, "tc: bad ntaps %d", L.ntaps);
+  FDX_REQUIRE(L.ntaps >= 1 && L.ntaps <= kTcMaxTaps, "tc: bad ntaps %d", L.ntaps);
   FDX_REQUIRE(L.es == 1 || L.es == 2, "tc: bad element stride %d", L.es);
   FDX_REQUIRE(L.Ncols > 0 && L.Ncols % 32 == 0, "tc: Ncols=%d must be a multiple of 32", L.Ncols);
   FDX_REQUIRE(L.A.strides[0] == 1 && L.B.strides[0] == 1, "tc: innermost strides must be 1");
@@ -449,7 +451,15 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
   TcDev d{};
   d.mode = L.mode;
   d.W = L.W; d.H = L.H; d.N = L.N; d.es = L.es; d.ntaps = L.ntaps;
-  for (int i = 0; i < 9; ++i) { d.tap_dx[i] = L.tap_dx[i]; d.tap_dy[i] = L.tap_dy[i]; d.tap_b[i] = L.tap_b[i]; }
+  d.es_b = L.es_b > 1 ? L.es_b : 1;
+  FDX_REQUIRE(d.es_b <= 2, "tc: bad B element stride %d", L.es_b);
+  bool b_view = d.es_b != 1;
+  for (int i = 0; i < kTcMaxTaps; ++i) {
+    d.tap_dx[i] = L.tap_dx[i]; d.tap_dy[i] = L.tap_dy[i]; d.tap_b[i] = L.tap_b[i];
+    d.tap_bdx[i] = L.tap_bdx[i]; d.tap_bdy[i] = L.tap_bdy[i];
+    b_view = b_view || L.tap_bdx[i] != 0 || L.tap_bdy[i] != 0;
+  }
+  FDX_REQUIRE(!b_view || L.mode == TC_MNMN, "tc: strided / shifted B views exist only in TC_MNMN");
   d.K = L.K; d.M = L.M; d.Ncols = L.Ncols; d.b_batched = L.b_batched; d.mn_batched = L.mn_batched;
   d.out = L.out; d.out_f32 = L.out_f32; d.out_atomic = L.out_atomic;
   d.os_x = L.os_x; d.os_y = L.os_y; d.os_n = L.os_n; d.os_tap = L.os_tap; d.os_m = L.os_m;
@@ -520,7 +530,7 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
     FDX_REQUIRE(!L.res || !L.out_atomic, "tc: residual with atomic output unsupported");
   } else {
     d.nblks = (L.Ncols + BN - 1) / BN;
-    d.tpp = (L.M <= 64 && L.ntaps > 1) ? 2 : 1;
+    d.tpp = (L.M <= 64 && L.ntaps > 1 && !b_view) ? 2 : 1;
     d.ntp = (L.ntaps + d.tpp - 1) / d.tpp;
     d.mblks = (L.M + 127) / 128;
     d.kchunks = 0;
@@ -573,7 +583,8 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
     } else if (L.mode == TC_KMN) {
       box[0] = 64; box[1] = 64; box[2] = 1; box[3] = 1;
     } else {
-      box[0] = 64; box[1] = (uint32_t)TW; box[2] = (uint32_t)TH; box[3] = (uint32_t)TN;
+      box[0] = 64; box[1] = (uint32_t)(TW * d.es_b); box[2] = (uint32_t)(TH * d.es_b); box[3] = (uint32_t)TN;
+      est[1] = est[2] = (uint32_t)d.es_b;
     }
     int s = fdx_make_tmap_bf16(&mB, L.B.ptr, 4, dims, str, box, est, 1);
     if (s != FDX_OK) return s;

@@ -23,16 +23,22 @@ enum TcMode {
   TC_MNMN = 2,   // A MN-major (m = channels, k = pixels), B MN-major  (wgrad-type)
 };
 
+constexpr int kTcMaxTaps = 16;   // 9 for a 3x3 conv, 16 = 4 phases x 2x2 taps of the sub-pixel upsample conv
+
 struct TcLaunch {
   int mode;
   TcOperand A, B;
   // logical output pixel space (x, y, n) for TC_KK/TC_KMN; reduction pixel space for TC_MNMN
   int W, H, N;
   int es;                 // element stride of the A read (1, or 2 for stride-2 conv)
-  int ntaps;              // 1..9
-  int tap_dx[9], tap_dy[9];   // A spatial offset of tap t (already includes -pad)
-  int tap_b[9];           // TC_KK: B z1 coordinate of tap t; TC_KMN: B row offset of tap t (elements of k);
+  int ntaps;              // 1..kTcMaxTaps
+  int tap_dx[kTcMaxTaps], tap_dy[kTcMaxTaps];   // A spatial offset of tap t (already includes -pad)
+  int tap_b[kTcMaxTaps];  // TC_KK: B z1 coordinate of tap t; TC_KMN: B row offset of tap t (elements of k);
                           // TC_MNMN: output slab index of tap t
+  // TC_MNMN only: the B operand may be a strided, shifted view of its tensor (element stride es_b,
+  // per-tap offset) - the output-parity view of dY in the sub-pixel upsample weight gradient
+  int es_b;               // 0/1 = dense, 2 = every other pixel
+  int tap_bdx[kTcMaxTaps], tap_bdy[kTcMaxTaps];
   int K;                  // channels per tap (TC_KK/TC_KMN); ignored for TC_MNMN
   int M;                  // TC_MNMN only: valid rows (channels of A)
   int Ncols;              // total output columns

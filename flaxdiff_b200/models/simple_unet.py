@@ -356,12 +356,13 @@ class Unet:
                 tape.append(("down", name, cur, dst))
                 cur = dst
             elif kind == "up":
-                u = ops.upsample2x(cur.t)
+                # nearest-2x + conv3x3 as four 2x2 parity convolutions of the low-resolution tensor
+                # (common.py:210-226); the upsampled activation is never materialised
                 h, w = h * 2, w * 2
                 dst = out_node(idx, h, w, cout)
-                ops.conv3x3_fwd(u, W16[name + "/ConvLayer_0/conv/kernel"],
-                                W[name + "/ConvLayer_0/conv/bias"], out=dst.t)
-                tape.append(("up", name, cur, dst, u if save else None))
+                weff = ops.upconv3x3_pack(W[name + "/ConvLayer_0/conv/kernel"])
+                ops.upconv3x3_fwd(cur.t, weff, W[name + "/ConvLayer_0/conv/bias"], dst.t)
+                tape.append(("up", name, cur, dst, weff if save else None))
                 cur = dst
             elif kind == "conv":
                 dst = out_node(idx, h, w, cout)
@@ -532,17 +533,15 @@ class Unet:
                 dx, acc = want(xin)
                 ops.conv3x3_dgrad(dy, W16[kn + "kernel"], dx, stride=2, accumulate=acc)
             elif kind == "up":
-                _, _, xin, dst, u = rec
+                _, _, xin, dst, weff = rec
                 dy = grad_of(dst)
                 kn = name + "/ConvLayer_0/conv/"
-                if u is None:
-                    u = ops.upsample2x(xin.t)
-                ops.conv3x3_wgrad(u, dy, Gd[kn + "kernel"])
+                if weff is None:
+                    weff = ops.upconv3x3_pack(W[kn + "kernel"])
+                ops.upconv3x3_wgrad(xin.t, dy, Gd[kn + "kernel"])
                 ops.colsum(dy, False, out=Gd[kn + "bias"])
-                du = torch.empty_like(u)
-                ops.conv3x3_dgrad(dy, W16[kn + "kernel"], du)
                 dx, acc = want(xin)
-                ops.upsample2x_bwd(du, dx, accumulate=acc)
+                ops.upconv3x3_dgrad(dy, weff, dx, accumulate=acc)
             elif kind == "conv_in":
                 _, _, x_bf16, dst = rec
                 dy = grad_of(dst)

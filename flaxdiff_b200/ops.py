@@ -326,6 +326,39 @@ def colsum(x: torch.Tensor, per_image: bool, out: Optional[torch.Tensor] = None)
     return out
 
 
+# --------------------------------------------------------------------------- upsample + conv (sub-pixel)
+def upconv3x3_pack(w_hwio: torch.Tensor) -> torch.Tensor:
+    """bf16 [16][Cin][Cout] parity/tap-summed weights of nearest-2x + conv3x3 from the f32 HWIO kernel."""
+    assert w_hwio.dtype == torch.float32 and w_hwio.is_contiguous() and w_hwio.shape[:2] == (3, 3)
+    cin, cout = w_hwio.shape[2], w_hwio.shape[3]
+    weff = torch.empty((16, cin, cout), dtype=torch.bfloat16, device=w_hwio.device)
+    check(load().fdx_upconv3x3_pack(ptr(w_hwio), ctypes.c_int(cin), ctypes.c_int(cout), ptr(weff), stream_ptr()),
+          "upconv3x3_pack")
+    return weff
+
+
+def upconv3x3_fwd(x: torch.Tensor, weff: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """out[B,2h,2w,Cout] = conv3x3_SAME(nearest2x(x)) + bias, without the upsampled tensor."""
+    check(load().fdx_upconv3x3_fwd(ctypes.byref(act(x, "x")), ptr(weff), ptr(bias), ctypes.byref(act(out, "out")),
+                                   stream_ptr()), "upconv3x3_fwd")
+    return out
+
+
+def upconv3x3_dgrad(dy: torch.Tensor, weff: torch.Tensor, dx: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+    check(load().fdx_upconv3x3_dgrad(ctypes.byref(act(dy, "dy")), ptr(weff), ctypes.byref(act(dx, "dx")),
+                                     ctypes.c_int(1 if accumulate else 0), stream_ptr()), "upconv3x3_dgrad")
+    return dx
+
+
+def upconv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, dw_hwio: torch.Tensor) -> torch.Tensor:
+    """Accumulates d(loss)/dw of the 3x3 kernel (f32 HWIO) into dw_hwio."""
+    assert dw_hwio.dtype == torch.float32 and dw_hwio.is_contiguous()
+    ws = torch.empty((16, x.shape[-1], dy.shape[-1]), dtype=torch.float32, device=x.device)
+    check(load().fdx_upconv3x3_wgrad(ctypes.byref(act(x, "x")), ctypes.byref(act(dy, "dy")), ptr(ws), ptr(dw_hwio),
+                                     stream_ptr()), "upconv3x3_wgrad")
+    return dw_hwio
+
+
 # --------------------------------------------------------------------------- 3-channel convs
 def conv_in_fwd(x_bf16: torch.Tensor, w: torch.Tensor, bias, out: torch.Tensor,
                 w_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:

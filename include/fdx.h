@@ -75,6 +75,21 @@ typedef struct {
  * and the QK^T / PV / backward products of nn.dot_product_attention (attention.py:170-174). */
 int fdx_gemm(const fdx_gemm_desc* g, void* stream);
 
+/* Upsample = jax.image.resize(nearest, x2) + ConvLayer 3x3 (models/common.py:210-226) without materialising
+ * the upsampled tensor: four output parities, each a 2x2 convolution of the LOW-resolution input with
+ * summed taps (4/9 of the FLOPs).  x / dx are the low-resolution tensors, y / dy the full-resolution ones.
+ *   fdx_upconv3x3_pack  : weff bf16 [4 parities][2][2][Cin][Cout] from the f32 HWIO master weights
+ *   fdx_upconv3x3_fwd   : y = conv3x3(nearest2x(x)) + bias
+ *   fdx_upconv3x3_dgrad : dx (+)= d/dx, one 16-tap launch
+ *   fdx_upconv3x3_wgrad : dw_hwio += d/dw; dweff_ws = f32 scratch of 16*Cin*Cout floats */
+int fdx_upconv3x3_pack(const float* w_hwio, int cin, int cout, void* weff_bf16, void* stream);
+int fdx_upconv3x3_fwd(const fdx_act* x, const void* weff_bf16, const float* bias, const fdx_act* y,
+                      void* stream);
+int fdx_upconv3x3_dgrad(const fdx_act* dy, const void* weff_bf16, const fdx_act* dx, int accumulate,
+                        void* stream);
+int fdx_upconv3x3_wgrad(const fdx_act* x, const fdx_act* dy, float* dweff_ws, float* dw_hwio,
+                        void* stream);
+
 /* ---- normalisation (HBM-bound; warp-shuffle + shared/global atomics reductions) ---- */
 /* nn.GroupNorm(groups, eps) statistics (models/common.py:273-281): stats[n][g] = (sum, sumsq), f32. */
 int fdx_groupnorm_stats(const fdx_act* x, int groups, float* stats, void* stream);

@@ -310,3 +310,39 @@ def test_upsample_colsum_add():
     o = torch.empty_like(x)
     ops.act_add(x, y, o)
     assert rel(o, x.float() + y.float()) < 4e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 128, 64), (3, 16, 16, 64, 128), (2, 4, 4, 512, 64), (2, 16, 8, 256, 192)])
+def test_upconv3x3_subpixel_fwd_dgrad_wgrad(shape):
+    """nearest-2x + conv3x3 (common.py:210-226) as four 2x2 parity convolutions: forward, data gradient
+    (plain and accumulating) and weight gradient against autograd on the fp32 oracle."""
+    torch.manual_seed(3)
+    B, h, w, cin, cout = shape
+    big = torch.randn(B, h, w, cin + 64, device=dev).bfloat16()
+    x = big[..., 64:]                                           # strided view (concat slot)
+    wt = torch.randn(3, 3, cin, cout, device=dev) / math.sqrt(9 * cin)
+    bias = torch.randn(cout, device=dev) * 0.1
+    weff = ops.upconv3x3_pack(wt)
+    ybig = torch.zeros(B, 2 * h, 2 * w, cout + 64, device=dev, dtype=torch.bfloat16)
+    y = ybig[..., :cout]
+    ops.upconv3x3_fwd(x, weff, bias, y)
+    xr = x.float().cpu().requires_grad_(True)
+    wr, br = wt.cpu().requires_grad_(True), bias.cpu().requires_grad_(True)
+    up = xr.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    yr = U.conv_same(up, wr, br)
+    assert rel(y, yr) < 6e-3
+    assert float(ybig[..., cout:].abs().max()) == 0.0           # neighbouring slot untouched
+    dy = torch.randn(B, 2 * h, 2 * w, cout, device=dev).bfloat16()
+    yr.backward(dy.float().cpu())
+    dx = torch.empty(B, h, w, cin, device=dev, dtype=torch.bfloat16)
+    ops.upconv3x3_dgrad(dy, weff, dx)
+    assert rel(dx, xr.grad) < 8e-3
+    base = torch.randn(B, h, w, cin, device=dev).bfloat16()
+    dx2 = base.clone()
+    ops.upconv3x3_dgrad(dy, weff, dx2, accumulate=True)
+    assert rel(dx2, xr.grad + base.float().cpu()) < 8e-3
+    dw = torch.zeros_like(wt)
+    ops.upconv3x3_wgrad(x, dy, dw)
+    assert rel(dw, wr.grad) < 5e-3
+    ops.upconv3x3_wgrad(x, dy, dw)                              # accumulates
+    assert rel(dw, 2 * wr.grad) < 5e-3
