@@ -11,6 +11,7 @@
 // fully coalesced; per-(image,group) partial sums are reduced with warp shuffles,
 // then shared-memory atomics, then one global atomic per block.
 #include "fdx_common.cuh"
+#include <stdlib.h>
 #include "../../include/fdx.h"
 
 namespace {
@@ -564,12 +565,16 @@ int gn_check(const fdx_act* x, int groups, const char* what) {
   return FDX_OK;
 }
 
-dim3 gn_grid(const fdx_act* x, int unroll, int vec = 8) {
+// Two waves of co-resident blocks (`resident` per SM for the kernel in question): every block then
+// amortises its prologue (statistics / gamma / beta loads) and epilogue (partial-sum reduction, atomics)
+// over many pixel rows.  Sizing for ~16 blocks per SM made the small deep-level tensors pure launch /
+// prologue latency (ncu: 8 MB in 8 us).
+dim3 gn_grid(const fdx_act* x, int unroll, int resident) {
   const int HW = x->h * x->w;
-  const int rows = kNT / (x->c / vec);
+  const int rows = kNT / (x->c / 8);
   int bx = (HW + rows * unroll - 1) / (rows * unroll);
-  // ~16 resident blocks per SM keeps enough 16-byte loads in flight to saturate HBM
-  int target = (16 * 148 + x->n - 1) / x->n;
+  static const int waves = getenv("FDX_GN_WAVES") ? atoi(getenv("FDX_GN_WAVES")) : 2;
+  int target = (waves * resident * 148) / x->n;
   if (target < 1) target = 1;
   if (bx > target) bx = target;
   if (bx < 1) bx = 1;
@@ -582,7 +587,7 @@ void launch_bwd_apply(const fdx_act* x, const fdx_act* dy, int groups, const flo
                       int accumulate, float* csum_img, cudaStream_t st) {
   const int C = x->c, HW = x->h * x->w;
   const size_t shm = csum_img ? sizeof(float) * (kNT / (C / 8)) * C : 0;
-  const dim3 grid = gn_grid(x, kBU);
+  const dim3 grid = gn_grid(x, kBU, accumulate ? 2 : 3);
   const __nv_bfloat16* xp = (const __nv_bfloat16*)x->ptr;
   const __nv_bfloat16* dp = (const __nv_bfloat16*)dy->ptr;
   __nv_bfloat16* op = (__nv_bfloat16*)dx->ptr;
@@ -613,7 +618,7 @@ int fdx_groupnorm_stats(const fdx_act* x, int groups, float* stats, void* stream
   if (s != FDX_OK) return s;
   cudaStream_t st = (cudaStream_t)stream;
   FDX_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * x->n, st));
-  gn_stats_kernel<<<gn_grid(x, kU), kNT, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pix_stride,
+  gn_stats_kernel<<<gn_grid(x, kU, 5), kNT, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pix_stride,
                                               x->h * x->w, x->c, groups, stats);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
@@ -626,11 +631,11 @@ int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const 
   FDX_REQUIRE(y && y->ptr && y->n == x->n && y->h == x->h && y->w == x->w && y->c == x->c,
               "groupnorm_apply: output shape mismatch");
   if (silu)
-    gn_apply_kernel<true><<<gn_grid(x, kU), kNT, 0, (cudaStream_t)stream>>>(
+    gn_apply_kernel<true><<<gn_grid(x, kU, 5), kNT, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x->ptr, x->pix_stride, x->h * x->w, x->c, groups, stats, gamma, beta, eps,
         (__nv_bfloat16*)y->ptr, y->pix_stride);
   else
-    gn_apply_kernel<false><<<gn_grid(x, kU), kNT, 0, (cudaStream_t)stream>>>(
+    gn_apply_kernel<false><<<gn_grid(x, kU, 5), kNT, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x->ptr, x->pix_stride, x->h * x->w, x->c, groups, stats, gamma, beta, eps,
         (__nv_bfloat16*)y->ptr, y->pix_stride);
   FDX_LAUNCH_CHECK();
@@ -655,11 +660,11 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
   FDX_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, st));
   const size_t shm = sizeof(float) * 2 * (kNT / (C / 8)) * C;
   if (silu)
-    gn_bwd_stats_kernel<true><<<gn_grid(x, kBU), kNT, shm, st>>>(
+    gn_bwd_stats_kernel<true><<<gn_grid(x, kBU, 3), kNT, shm, st>>>(
         (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, HW, C,
         groups, stats, gamma, beta, eps, sums);
   else
-    gn_bwd_stats_kernel<false><<<gn_grid(x, kBU), kNT, shm, st>>>(
+    gn_bwd_stats_kernel<false><<<gn_grid(x, kBU, 3), kNT, shm, st>>>(
         (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, HW, C,
         groups, stats, gamma, beta, eps, sums);
   FDX_LAUNCH_CHECK();

@@ -64,7 +64,32 @@ def gn_fusion(res, B):
     print(f"TOTAL | {t[0]:7.3f} {t[1]:7.3f} = {t[0]+t[1]:7.3f} | {t[2]:7.3f} {t[3]:7.3f} = {t[2]+t[3]:7.3f}", flush=True)
 
 
+def gn_only(res, B):
+    """GroupNorm forward / backward streaming rates over the UNet's tensor sizes."""
+    tot = [0.0, 0.0, 0.0]
+    for c, r in ((64, res), (128, res), (320, res), (128, res // 2), (192, res // 2), (576, res // 2),
+                 (256, res // 4), (384, res // 4), (512, res // 4), (512, res // 8), (768, res // 8), (1024, res // 8)):
+        x = (torch.randn(B, r, r, c, device=dev) * 1.5 + 0.3).bfloat16()
+        dy = torch.randn(B, r, r, c, device=dev).bfloat16()
+        dx = torch.empty_like(x)
+        g, b = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+        dg, db = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+        st = ops.groupnorm_stats(x, 8)
+        y = torch.empty_like(x)
+        m1 = timeit(lambda: ops.groupnorm_stats(x, 8))
+        m2 = timeit(lambda: ops.groupnorm_apply(x, 8, st, g, b, 1e-4, True, out=y))
+        m3 = timeit(lambda: ops.groupnorm_bwd(x, dy, 8, st, g, b, 1e-4, True, dg, db, dx))
+        nb = x.numel() * 2 / 1e6
+        for i, m in enumerate((m1, m2, m3)):
+            tot[i] += m
+        print(f"GN {r:3d}x{r:<3d}x{c:<4d} {nb:7.1f} MB | stats {m1*1e3:7.1f} us {nb/m1/1e3:5.2f} TB/s | apply {m2*1e3:7.1f} us "
+              f"{2*nb/m2/1e3:5.2f} TB/s | bwd {m3*1e3:7.1f} us {5*nb/m3/1e3:5.2f} TB/s", flush=True)
+    print(f"TOTAL stats {tot[0]:.3f} ms apply {tot[1]:.3f} ms bwd {tot[2]:.3f} ms", flush=True)
+
+
 def main():
+    if len(sys.argv) > 3 and sys.argv[3] == "gnonly":
+        return gn_only(int(sys.argv[1]), int(sys.argv[2]))
     if len(sys.argv) > 3 and sys.argv[3] == "gn":
         return gn_fusion(int(sys.argv[1]), int(sys.argv[2]))
     res = int(sys.argv[1]) if len(sys.argv) > 1 else 64
