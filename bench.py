@@ -67,6 +67,25 @@ def load_peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else any library prints there (NCCL's version banner,
+    for one) is sent to stderr for the rest of the run."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def roofline_traffic(workload: str, batch: int) -> dict:
     """DRAM bytes the tensor-core engine moved in one step, from the committed ncu pass (profiles/) of the
     same workload; null when no capture exists for this workload / batch."""
@@ -183,7 +202,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------ this repo
@@ -194,6 +213,7 @@ def log(msg):
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -378,7 +398,7 @@ def main():
     }
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, model, res, acfg)
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -464,7 +484,7 @@ def run_sampling(args):
                             "achieved": head["tensor_frac_of_sustained"] * tf_sust, "peak": tf_sust, "unit": "TFLOP/s",
                             "frac": head["tensor_frac_of_sustained"], "peak_source": f"{src} bf16_tflops_sustained",
                             "traffic": None}}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
