@@ -31,6 +31,10 @@ class fdx_act(ctypes.Structure):
     ]
 
 
+class fdx_colstats(ctypes.Structure):
+    _fields_ = [("ws", ctypes.c_void_p), ("slots", ctypes.c_int), ("ld", ctypes.c_int)]
+
+
 class fdx_gemm_desc(ctypes.Structure):
     _fields_ = [
         ("mode", ctypes.c_int),

@@ -33,8 +33,9 @@ int check_act(const fdx_act* a, const char* name) {
 
 extern "C" {
 
-int fdx_conv3x3_fwd(const fdx_act* x, const void* w_hwio, const float* bias, const float* rowvec,
-                    const fdx_act* res, const fdx_act* y, int stride, void* stream) {
+static int conv3x3_fwd_impl(const fdx_act* x, const void* w_hwio, const float* bias, const float* rowvec,
+                            const fdx_act* res, const fdx_act* y, int stride, const fdx_colstats* cs,
+                            void* stream) {
   int s;
   if ((s = check_act(x, "conv3x3_fwd x")) != FDX_OK) return s;
   if ((s = check_act(y, "conv3x3_fwd y")) != FDX_OK) return s;
@@ -78,8 +79,27 @@ int fdx_conv3x3_fwd(const fdx_act* x, const void* w_hwio, const float* bias, con
     L.rs_x = res->pix_stride; L.rs_y = res->pix_stride * res->w;
     L.rs_n = res->pix_stride * res->w * res->h;
   }
+  if (cs) {
+    FDX_REQUIRE(cs->ws && cs->slots > 0 && cs->slots <= 64 && cs->ld >= y->c, "conv3x3_fwd_stats: bad workspace");
+    L.gn_ws = cs->ws;
+    L.gn_slots = cs->slots;
+    L.ws_ld = cs->ld;
+  }
   return fdx_tc_launch(L, (cudaStream_t)stream);
 }
+
+int fdx_conv3x3_fwd(const fdx_act* x, const void* w_hwio, const float* bias, const float* rowvec,
+                    const fdx_act* res, const fdx_act* y, int stride, void* stream) {
+  return conv3x3_fwd_impl(x, w_hwio, bias, rowvec, res, y, stride, nullptr, stream);
+}
+
+int fdx_conv3x3_fwd_stats(const fdx_act* x, const void* w_hwio, const float* bias, const float* rowvec,
+                          const fdx_act* res, const fdx_act* y, int stride, const fdx_colstats* cs,
+                          void* stream) {
+  FDX_REQUIRE(cs, "conv3x3_fwd_stats: null statistics descriptor");
+  return conv3x3_fwd_impl(x, w_hwio, bias, rowvec, res, y, stride, cs, stream);
+}
+
 
 int fdx_conv3x3_dgrad(const fdx_act* dy, const void* w_hwio, const fdx_act* dx, int stride,
                       int accumulate, void* stream) {

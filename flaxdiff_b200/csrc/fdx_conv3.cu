@@ -179,8 +179,8 @@ fdx_conv3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       };
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       {
-        EpiArgs ea{p.out, p.bias, p.rowvec, p.res, p.Ncols, 1.f, nullptr, nullptr, 0};
-        epilogue_bf16_coalesced<BN, false>(ea, epi_stage + q * 4096, t_addr, lane, nt * BN, valid, obase, rbase,
+        EpiArgs ea{p.out, p.bias, p.rowvec, p.res, p.Ncols, 1.f, nullptr, nullptr, 0, 0};
+        epilogue_bf16_coalesced<BN, EPI_PLAIN, 1>(ea, epi_stage + q * 4096, t_addr, lane, nt * BN, valid, obase, rbase,
                                            n, wait_acc);
       }
       tc_fence_before();

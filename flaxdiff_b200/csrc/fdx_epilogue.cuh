@@ -11,7 +11,12 @@
 // warp waits for the accumulator, and that of chunk c+1 while chunk c is being converted, so its
 // global-memory latency never sits on the epilogue's critical path.
 //
-// GN = true fuses the first pass of GroupNorm(+SiLU) backward (flaxdiff/models/common.py:286-288,
+// EPI = EPI_COLSTATS additionally accumulates, per (image, output channel), the sum and the sum of
+// squares of the bf16 values it stores: the statistics pass of the GroupNorm that consumes this tensor
+// (flaxdiff/models/common.py:273-288) then never reads it (2 B/element saved; two fused multiply-adds
+// per element in the coalesced store phase - cheap enough for the four epilogue warps, unlike silu').
+//
+// EPI = EPI_GN_BWD fuses the first pass of GroupNorm(+SiLU) backward (flaxdiff/models/common.py:286-288,
 // 310-312 under jax.grad) into the data-gradient convolution that produces its input: with
 // z = a_c x + b_c (a_c = rstd*gamma_c, b_c = beta_c - mean*a_c, per image) the kernel writes
 // dz = dy * silu'(z) instead of dy and accumulates the two per-(image, channel) sums the backward
@@ -26,11 +31,14 @@ struct EpiArgs {
   const void* res;         // bf16 or null (GN: the GroupNorm input x)
   int Ncols;
   float alpha;
-  // ---- GN fusion only ----
-  const float* gn_ab;      // [N][2][Ncols]: a then b
-  float* gn_ws;            // [slots][N][2][Ncols]: S0 then S1, f32 atomics
+  // ---- EPI_GN_BWD / EPI_COLSTATS only ----
+  const float* gn_ab;      // EPI_GN_BWD: [N][2][Ncols]: a then b
+  float* gn_ws;            // [slots][N][2][ws_ld] f32 atomics: (sum dz, sum dz*x) or (sum y, sum y*y)
   int gn_N;                // images
+  int ws_ld;               // channels per row of gn_ws (the destination BUFFER's channel count)
 };
+
+enum { EPI_PLAIN = 0, EPI_GN_BWD = 1, EPI_COLSTATS = 2 };
 
 __device__ __forceinline__ uint32_t epi_swz(int row, int piece) {   // byte offset inside a warp's 4 KB tile
   return (uint32_t)(row * 128 + ((piece ^ (row & 7)) << 4));
@@ -50,12 +58,14 @@ __device__ __forceinline__ float epi_silu_grad_times(float dy, float z) {
 //   GN only : q = warp quarter (0..3), xchg = 2 x 2 KB CTA-shared exchange area, par = running chunk
 //             parity (kept by the caller across tiles), slot = workspace slot of this tile; all rows
 //             of the tile belong to image `img` of lane 0.
-template <int BN, bool GN, class WaitFn>
+template <int BN, int EPI, int PARTS, class WaitFn>
 __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_t* stage, uint32_t t_addr,
                                                        int lane, int col_base, bool valid, long long obase,
                                                        long long rbase, int img, WaitFn wait_acc, int q = 0,
                                                        float* xchg = nullptr, int* par = nullptr,
                                                        int slot = 0) {
+  constexpr bool GN = (EPI == EPI_GN_BWD);
+  constexpr bool SUMS = (EPI != EPI_PLAIN);
   const uint32_t sbase = smem_u32(stage);
   const int sub = lane >> 3, piece = lane & 7;       // coalesced phase: 4 rows x 8 pieces per instruction
   const bool side = (e.res != nullptr);
@@ -114,7 +124,16 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
       tmem_ld_wait();
       float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * e.alpha;
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+#pragma unroll
+      for (int pp = 1; pp < PARTS; ++pp) {             // partial accumulators (see TcCfg::kParts)
+        tmem_ld_32x32(t_addr + pp * BN + c0 + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] *= e.alpha;
       if (e.bias) {
         const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0 + h * 32);
 #pragma unroll
@@ -173,7 +192,7 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
     __syncwarp();
     // ---- shared -> global, coalesced (GN: plus the column sums of dz and dz*x) ---------------------
     float s0[8], s1[8];
-    if constexpr (GN) {
+    if constexpr (SUMS) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
     }
@@ -185,12 +204,14 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
                    : "memory");
       const bool live = ((ok_mask >> k) & 1u) && (piece < 4 || half2);
       if (live) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(e.out) + ob_k[k] + col0 + piece * 8) = u;
-      if constexpr (GN) {
+      if constexpr (SUMS) {
         if (live) {
           const float2 d0 = unpack_bf16x2(u.x), d1 = unpack_bf16x2(u.y), d2 = unpack_bf16x2(u.z),
                        d3 = unpack_bf16x2(u.w);
-          const float2 x0 = unpack_bf16x2(xr[k].x), x1 = unpack_bf16x2(xr[k].y), x2 = unpack_bf16x2(xr[k].z),
-                       x3 = unpack_bf16x2(xr[k].w);
+          // second factor: the GroupNorm input x (EPI_GN_BWD) or the stored value itself (EPI_COLSTATS)
+          const uint4 xq = GN ? xr[k] : u;
+          const float2 x0 = unpack_bf16x2(xq.x), x1 = unpack_bf16x2(xq.y), x2 = unpack_bf16x2(xq.z),
+                       x3 = unpack_bf16x2(xq.w);
           s0[0] += d0.x; s0[1] += d0.y; s0[2] += d1.x; s0[3] += d1.y;
           s0[4] += d2.x; s0[5] += d2.y; s0[6] += d3.x; s0[7] += d3.y;
           s1[0] = fmaf(d0.x, x0.x, s1[0]); s1[1] = fmaf(d0.y, x0.y, s1[1]);
@@ -200,7 +221,7 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
         }
       }
     }
-    if constexpr (GN) {
+    if constexpr (SUMS) {
       // rows of this warp: combine the four `sub` lane groups; lanes 0..7 then own 8 channels each
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -228,7 +249,7 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
           t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
         }
         if (c4 < 32 || half2) {
-          float* dst = e.gn_ws + (((long long)slot * e.gn_N + img0) * 2 + which) * e.Ncols + col0 + c4;
+          float* dst = e.gn_ws + (((long long)slot * e.gn_N + img0) * 2 + which) * e.ws_ld + col0 + c4;
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y),
                        "f"(t.z), "f"(t.w)
                        : "memory");

@@ -336,6 +336,27 @@ gn_collapse_slots_kernel(const float* __restrict__ wsl, int slots, int N, int C,
   }
 }
 
+// stats[n][g] = (sum, sumsq) from the per-(image, channel) sums a convolution epilogue accumulated:
+// cols[slot][n][{0,1}][C]; one warp per (image, group)
+__global__ void __launch_bounds__(256)
+gn_stats_from_cols_kernel(const float* __restrict__ cols, int slots, int N, int ld, int c0, int C, int G,
+                          float* __restrict__ stats) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= N * G) return;
+  const int lane = threadIdx.x & 31, n = i / G, g = i % G, cpg = C / G;
+  float s = 0.f, q = 0.f;
+  for (int sl = 0; sl < slots; ++sl) {
+    const float* b = cols + (((long long)sl * N + n) * 2) * ld + c0 + g * cpg;
+    for (int c = lane; c < cpg; c += 32) { s += b[c]; q += b[ld + c]; }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    stats[(long long)n * 2 * G + 2 * g] = s;
+    stats[(long long)n * 2 * G + 2 * g + 1] = q;
+  }
+}
+
 // out[c] (+)= sum_r in[r][c]; 32 columns x 8 row lanes per block
 __global__ void __launch_bounds__(256)
 reduce_rows_kernel(const float* __restrict__ in, int R, int C, float* __restrict__ out, int accumulate) {
@@ -620,6 +641,17 @@ int fdx_groupnorm_stats(const fdx_act* x, int groups, float* stats, void* stream
   FDX_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * x->n, st));
   gn_stats_kernel<<<gn_grid(x, kU, 5), kNT, 0, st>>>((const __nv_bfloat16*)x->ptr, x->pix_stride,
                                               x->h * x->w, x->c, groups, stats);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+int fdx_groupnorm_stats_from_cols(const float* cols, int slots, int N, int ld, int c0, int C, int groups,
+                                  float* stats, void* stream) {
+  FDX_REQUIRE(cols && stats && slots > 0 && N > 0 && C > 0 && groups > 0 && C % groups == 0 && c0 >= 0 &&
+                  c0 + C <= ld,
+              "groupnorm_stats_from_cols: bad arguments");
+  gn_stats_from_cols_kernel<<<(N * groups + 7) / 8, 256, 0, (cudaStream_t)stream>>>(cols, slots, N, ld, c0, C,
+                                                                                    groups, stats);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

@@ -39,7 +39,13 @@ struct TcCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
                                     16384 /*epilogue staging: 4 warps x 4 KB*/ +
                                     4096 /*GroupNorm-backward column-sum exchange*/;
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // Every M=128,K=16 MMA with a K-major A operand costs ~150 cycles whatever N is (tensor pipe 21 %
+  // active at N=64, 43 % at 128, 85 % at 256).  Cycling through kParts independent partial accumulators
+  // (summed by the epilogue) was measured NOT to help (4 / 2 parts at BN = 64 / 128: 26.4 vs 25.9 ms per
+  // step), so the cost is not an accumulator dependency chain; neither is it B's shared-memory traffic
+  // (CTA pairs, below).  The mechanism is kept for experiments.
+  static constexpr int kParts = 1;
+  static constexpr int kTmemCols = 512;     // 2 buffers x kParts x BN columns
 };
 
 struct TcDev {
@@ -62,6 +68,7 @@ struct TcDev {
   int ntp;               // TC_MNMN: number of tap groups = ceil(ntaps / tpp)
   int splits;
   int ntiles;
+  int npairs;            // PAIR kernels: ceil(row tiles / 2) * nblks tile pairs
   // epilogue
   void* out;
   int out_f32, out_atomic;
@@ -75,6 +82,7 @@ struct TcDev {
   const float* gn_ab;
   float* gn_ws;
   int gn_slots;
+  int ws_ld;               // row length of gn_ws (EPI_COLSTATS: channels of the destination buffer)
 };
 
 // TC_MNMN tile decode: tile -> (batch block bz, split, nt, mb, tap) and the K range [pb0, pb1)
@@ -98,11 +106,26 @@ __device__ __forceinline__ MnTile decode_mn(const TcDev& p, int tile) {
   return m;
 }
 
-template <int BN, int MODE, bool GN>
+// PAIR = true: the kernel runs as clusters of two CTAs (one TPC).  Each CTA owns one 128-row tile and
+// stages its own A box plus HALF of the B tile's columns; the leader CTA (cluster rank 0) issues
+// tcgen05.mma.cta_group::2 (M = 256) that reads both CTAs' shared memory and writes both CTAs' TMEM.
+// B's TMA writes and UMMA reads per CTA are halved - the engine's measured bound is shared-memory
+// bandwidth.  Barrier topology: every TMA of either CTA completes on the LEADER's full[stage]; the
+// leader's commits multicast to empty[stage] / tfull[acc] of both CTAs; both CTAs' epilogue warps
+// arrive on the leader's tempty[acc].
+template <int BN, int MODE, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
               const TcDev p) {
   using Cfg = TcCfg<BN>;
+  static_assert(!PAIR || MODE != TC_MNMN, "CTA pairs: K-major A only");
+  constexpr int BNL = PAIR ? BN / 2 : BN;           // B columns staged by THIS CTA
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+  // tile loop of this CTA: index t -> (column block nt, row tile mt)
+  const int t_begin = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int t_step = PAIR ? (int)cluster_nctaid_x() : (int)gridDim.x;
+  const int t_end = PAIR ? p.npairs : p.ntiles;
   constexpr int S = Cfg::kStages;
   constexpr bool A_MN = (MODE == TC_MNMN);
   constexpr bool B_MN = (MODE != TC_KK);
@@ -133,16 +156,16 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 4);
-    mbar_init(&tempty[1], 4);
+    mbar_init(&tempty[0], PAIR ? 8 : 4);
+    mbar_init(&tempty[1], PAIR ? 8 : 4);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, Cfg::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -155,10 +178,10 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
         if constexpr (!A_MN) {
           const int nt = tile % p.nblks;
-          const int mt = tile / p.nblks;
+          const int mt = PAIR ? 2 * (tile / p.nblks) + (int)rank : tile / p.nblks;
           const int xb = mt % p.nxb;
           const int yb = (mt / p.nxb) % p.nyb;
           const int nb = mt / (p.nxb * p.nyb);
@@ -170,11 +193,28 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa0 = smem + stage * Cfg::kStageBytes;
             uint8_t* sb0 = sa0 + SUB * kABytes;
-            mbar_arrive_expect_tx(&full[stage], nsub * (kABytes + Cfg::kBBytes));
+            if constexpr (PAIR) {
+              // the leader posts the bytes of BOTH CTAs; the peer's loads complete on the same barrier
+              if (leader) mbar_arrive_expect_tx(&full[stage], nsub * (2 * kABytes + Cfg::kBBytes));
+            } else {
+              mbar_arrive_expect_tx(&full[stage], nsub * (kABytes + Cfg::kBBytes));
+            }
             for (int u = 0; u < nsub; ++u) {
               const int t = (q + u) / p.kchunks, kc = (q + u) % p.kchunks;
               uint8_t* sa = sa0 + u * kABytes;
               uint8_t* sb = sb0 + u * Cfg::kBBytes;
+              const int ncol0 = nt * BN + (int)rank * BNL;      // first B column staged by this CTA
+              if constexpr (PAIR) {
+                tma_load_4d_2sm(sa, &mapA, &full[stage], kc * kBK, x0 + p.tap_dx[t], y0 + p.tap_dy[t], n0);
+                if constexpr (!B_MN) {
+                  tma_load_4d_2sm(sb, &mapB, &full[stage], kc * kBK, ncol0, p.b_batched ? zb1 : p.tap_b[t], zb2);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < BNL / 64; ++j)
+                    tma_load_4d_2sm(sb + j * (kBK * 128), &mapB, &full[stage], ncol0 + j * 64,
+                                    p.tap_b[t] + kc * kBK, zb1, zb2);
+                }
+              } else {
               tma_load_4d(sa, &mapA, &full[stage], kc * kBK, x0 + p.tap_dx[t], y0 + p.tap_dy[t], n0);
               if constexpr (!B_MN) {
                 // B K-major: box (64 k, BN rows); tap selects z1 (or batched z1/z2)
@@ -186,6 +226,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 for (int j = 0; j < BN / 64; ++j)
                   tma_load_4d(sb + j * (kBK * 128), &mapB, &full[stage], nt * BN + j * 64,
                               p.tap_b[t] + kc * kBK, zb1, zb2);
+              }
               }
             }
             if (++stage == S) { stage = 0; phase ^= 1; }
@@ -227,13 +268,13 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
         int nk;
         if constexpr (!A_MN) {
           nk = p.ntaps * p.kchunks;
@@ -243,7 +284,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::kParts * BN);
         for (int q = 0; q < nk; q += SUBK) {
           const int nsub = (nk - q) < SUBK ? (nk - q) : SUBK;
           mbar_wait(&full[stage], phase);
@@ -261,16 +302,23 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                                        : umma_desc_sw128(sa + k * 32, 16, 1024);
               const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, kBK * 128, 1024)
                                        : umma_desc_sw128(sb + k * 32, 16, 1024);
-              umma_f16(d_tmem, da, db, idesc, ((q + u) | k) != 0 ? 1u : 0u);
+              // MMA number (q+u)*4 + k of this tile goes to partial accumulator (number % kParts);
+              // the first MMA of every partial overwrites it
+              const int mi = (q + u) * (kBK / 16) + k;
+              const uint32_t dpart = d_tmem + (uint32_t)((mi % Cfg::kParts) * BN);
+              const uint32_t accf = mi >= Cfg::kParts ? 1u : 0u;
+              if constexpr (PAIR) umma_f16_2sm(dpart, da, db, idesc, accf);
+              else umma_f16(dpart, da, db, idesc, accf);
             }
           }
-          umma_commit(&empty[stage]);   // frees the smem stage when these MMAs retire
+          // frees the smem stage (of both CTAs of a pair) when these MMAs retire
+          if constexpr (PAIR) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
         if (nk == 0) {
           // nothing accumulated for this tile: epilogue must not read garbage
         }
-        umma_commit(&tfull[acc]);
+        if constexpr (PAIR) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -281,7 +329,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     int gn_par = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    for (int tile = t_begin; tile < t_end; tile += t_step) {
       int nt;
       bool valid;
       long long obase, rbase = 0;
@@ -289,7 +337,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       bool has_acc = true;
       if constexpr (!A_MN) {
         nt = tile % p.nblks;
-        const int mt = tile / p.nblks;
+        const int mt = PAIR ? 2 * (tile / p.nblks) + (int)rank : tile / p.nblks;
         const int xb = mt % p.nxb;
         const int yb = (mt / p.nxb) % p.nyb;
         const int nb = mt / (p.nxb * p.nyb);
@@ -315,13 +363,13 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
       };
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::kParts * BN);
       if (!A_MN && !p.out_f32 && !p.out_atomic) {
         // bf16 output: stage through shared memory so global stores / side-input loads are coalesced
-        EpiArgs ea{p.out, p.bias, p.rowvec, p.res, p.Ncols, p.alpha, p.gn_ab, p.gn_ws, p.N};
-        epilogue_bf16_coalesced<BN, GN>(ea, epi_stage + q * 4096, t_addr, lane, nt * BN, valid && has_acc,
-                                        obase, rbase, img, wait_acc, q, epi_xchg, &gn_par,
-                                        GN ? tile % p.gn_slots : 0);
+        EpiArgs ea{p.out, p.bias, p.rowvec, p.res, p.Ncols, p.alpha, p.gn_ab, p.gn_ws, p.N, p.ws_ld};
+        epilogue_bf16_coalesced<BN, EPI, Cfg::kParts>(ea, epi_stage + q * 4096, t_addr, lane, nt * BN, valid && has_acc,
+                                         obase, rbase, img, wait_acc, q, epi_xchg, &gn_par,
+                                         EPI != EPI_PLAIN ? tile % p.gn_slots : 0);
       } else {
       wait_acc();
 #pragma unroll 1
@@ -329,11 +377,20 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         uint32_t v[32];
         tmem_ld_32x32(t_addr + c0, v);
         tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+#pragma unroll
+        for (int pp = 1; pp < Cfg::kParts; ++pp) {        // sum the partial accumulators
+          tmem_ld_32x32(t_addr + pp * BN + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+        }
         const int col0 = nt * BN + c0;
         if (valid && has_acc && col0 < p.Ncols) {
-          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+          for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
@@ -382,42 +439,82 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(&tempty[acc], 0); else mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();   // the leader's MMAs read the peer's smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int MODE, bool GN>
+template <int BN, int MODE, int EPI>
 int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d, cudaStream_t stream) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    FDX_CUDA(cudaFuncSetAttribute(fdx_tc_kernel<BN, MODE, GN>,
+    FDX_CUDA(cudaFuncSetAttribute(fdx_tc_kernel<BN, MODE, EPI, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   int grid = fdx_num_sms();
   if (grid <= 0) return FDX_ERR_NO_DEVICE;
   if (d.ntiles < grid) grid = d.ntiles;
-  fdx_tc_kernel<BN, MODE, GN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA, mB, d);
+  fdx_tc_kernel<BN, MODE, EPI, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA, mB, d);
   FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+// CTA-pair launch: clusters of two CTAs, an even grid
+template <int BN, int MODE>
+int launch_pair(const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d, cudaStream_t stream) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FDX_CUDA(cudaFuncSetAttribute(fdx_tc_kernel<BN, MODE, EPI_PLAIN, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  int sms = fdx_num_sms();
+  if (sms <= 0) return FDX_ERR_NO_DEVICE;
+  int clusters = sms / 2;
+  if (d.npairs < clusters) clusters = d.npairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FDX_CUDA(cudaLaunchKernelEx(&cfg, fdx_tc_kernel<BN, MODE, EPI_PLAIN, true>, mA, mB, d));
+  fdx_count_launch();
   return FDX_OK;
 }
 
 template <int BN, int MODE>
 int launch_gn(const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d, cudaStream_t stream) {
   if constexpr (MODE == TC_KK) {
-    if (d.gn_ab) return launch_cfg<BN, MODE, true>(mA, mB, d, stream);
+    if (d.gn_ab) return launch_cfg<BN, MODE, EPI_GN_BWD>(mA, mB, d, stream);
   }
-  return launch_cfg<BN, MODE, false>(mA, mB, d, stream);
+  if constexpr (MODE == TC_KMN) {
+    if (d.gn_ws && !d.gn_ab) return launch_cfg<BN, MODE, EPI_COLSTATS>(mA, mB, d, stream);
+  }
+  if constexpr (MODE != TC_MNMN && BN >= 128 && !(MODE == TC_KMN && BN == 192)) {
+    if (d.npairs > 0) return launch_pair<BN, MODE>(mA, mB, d, stream);
+  }
+  return launch_cfg<BN, MODE, EPI_PLAIN>(mA, mB, d, stream);
 }
 
 template <int MODE>
@@ -466,6 +563,11 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
   d.alpha = L.alpha; d.bias = L.bias; d.rowvec = L.rowvec; d.res = L.res;
   d.rs_x = L.rs_x; d.rs_y = L.rs_y; d.rs_n = L.rs_n;
   d.gn_ab = L.gn_ab; d.gn_ws = L.gn_ws; d.gn_slots = L.gn_slots > 0 ? L.gn_slots : 1;
+  d.ws_ld = L.ws_ld > 0 ? L.ws_ld : L.Ncols;
+  if (L.gn_ws && !L.gn_ab) {
+    FDX_REQUIRE(L.mode == TC_KMN && !L.gemm_like && !L.out_f32 && !L.out_atomic,
+                "tc: output column statistics need a bf16 convolution-forward launch");
+  }
   if (L.gn_ab) {
     FDX_REQUIRE(L.mode == TC_KK && !L.gemm_like && L.res && L.gn_ws && !L.out_f32 && !L.out_atomic &&
                     !L.bias && !L.rowvec,
@@ -502,8 +604,8 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
     TN = 1;
   }
   d.TW = TW; d.TH = TH; d.TN = TN;
-  if (L.gn_ab && TN != 1) {
-    fdx_set_error("tc: GroupNorm-backward fusion needs at least 128 pixels per image (got %dx%d)", L.W, L.H);
+  if (L.gn_ws && TN != 1) {
+    fdx_set_error("tc: fused per-image column sums need at least 128 pixels per image (got %dx%d)", L.W, L.H);
     return FDX_ERR_UNSUPPORTED;
   }
   d.nxb = (L.W + TW - 1) / TW;
@@ -513,7 +615,7 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
 
   // halo-sharing variant: fewer TMA writes, but measured slower than the generic kernel on B200
   // (both are shared-memory-bandwidth bound); kept as an opt-in experiment.
-  if (L.mode != TC_MNMN && !L.gn_ab && getenv("FDX_CONV3")) {
+  if (L.mode != TC_MNMN && !L.gn_ws && getenv("FDX_CONV3")) {
     const int r3 = fdx_conv3_launch(L, BN, stream);
     if (r3 != FDX_ERR_UNSUPPORTED) return r3;
   }
@@ -523,6 +625,11 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
     d.nblks = (L.Ncols + BN - 1) / BN;
     d.kchunks = (L.K + kBK - 1) / kBK;
     d.ntiles = (int)(pix_blocks * d.nblks);
+    // CTA pairs (cta_group::2): plain bf16 epilogue, BN >= 128 (MN-major B needs whole 64-column blocks
+    // per CTA: not BN = 192); opt-in while it is being measured
+    d.npairs = 0;
+    if (getenv("FDX_PAIR") && !L.gn_ws && BN >= 128 && !(L.mode == TC_KMN && BN == 192) && pix_blocks >= 2)
+      d.npairs = (int)(((pix_blocks + 1) / 2) * d.nblks);
     d.splits = 1;
     d.mblks = 1;
     d.tpp = 1;
@@ -579,7 +686,7 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
     uint32_t box[4];
     uint32_t est[4] = {1, 1, 1, 1};
     if (L.mode == TC_KK) {
-      box[0] = 64; box[1] = (uint32_t)BN; box[2] = 1; box[3] = 1;
+      box[0] = 64; box[1] = (uint32_t)(d.npairs > 0 ? BN / 2 : BN); box[2] = 1; box[3] = 1;
     } else if (L.mode == TC_KMN) {
       box[0] = 64; box[1] = 64; box[2] = 1; box[3] = 1;
     } else {

@@ -102,8 +102,8 @@ int fdx_upconv3x3_pack(const float* w_hwio, int cin, int cout, void* weff_bf16, 
   return FDX_OK;
 }
 
-int fdx_upconv3x3_fwd(const fdx_act* x, const void* weff_bf16, const float* bias, const fdx_act* y,
-                      void* stream) {
+static int upconv_fwd_impl(const fdx_act* x, const void* weff_bf16, const float* bias, const fdx_act* y,
+                           const fdx_colstats* cs, void* stream) {
   int s = check_pair(x, y, "upconv3x3_fwd");
   if (s != FDX_OK) return s;
   FDX_REQUIRE(weff_bf16, "upconv3x3_fwd: null weights");
@@ -134,10 +134,28 @@ int fdx_upconv3x3_fwd(const fdx_act* x, const void* weff_bf16, const float* bias
     L.os_x = 2 * y->pix_stride; L.os_y = 2 * y->pix_stride * y->w; L.os_n = y->pix_stride * y->w * y->h;
     L.alpha = 1.f;
     L.bias = bias;
+    if (cs) {   // the four parities add their quarter of the pixels to the same sums
+      FDX_REQUIRE(cs->ws && cs->slots > 0 && cs->slots <= 64 && cs->ld >= y->c,
+                  "upconv3x3_fwd_stats: bad workspace");
+      L.gn_ws = cs->ws;
+      L.gn_slots = cs->slots;
+      L.ws_ld = cs->ld;
+    }
     s = fdx_tc_launch(L, (cudaStream_t)stream);
     if (s != FDX_OK) return s;
   }
   return FDX_OK;
+}
+
+int fdx_upconv3x3_fwd(const fdx_act* x, const void* weff_bf16, const float* bias, const fdx_act* y,
+                      void* stream) {
+  return upconv_fwd_impl(x, weff_bf16, bias, y, nullptr, stream);
+}
+
+int fdx_upconv3x3_fwd_stats(const fdx_act* x, const void* weff_bf16, const float* bias, const fdx_act* y,
+                            const fdx_colstats* cs, void* stream) {
+  FDX_REQUIRE(cs, "upconv3x3_fwd_stats: null statistics descriptor");
+  return upconv_fwd_impl(x, weff_bf16, bias, y, cs, stream);
 }
 
 int fdx_upconv3x3_dgrad(const fdx_act* dy, const void* weff_bf16, const fdx_act* dx, int accumulate,

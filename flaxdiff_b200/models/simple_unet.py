@@ -27,6 +27,7 @@ Execution design (B200-first, not a translation of the flax module tree):
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -43,14 +44,42 @@ ATTN_EPS = 1e-4     # TransformerBlock.norm_epsilon, models/attention.py:319
 
 
 class Node:
-    """An activation view plus (lazily) its gradient view."""
-    __slots__ = ("t", "g", "gw", "parent")
+    """An activation view plus (lazily) its gradient view.  `cs` / `coff` / `cs_ok`: the buffer's
+    per-image channel-sum workspace (ops.ColStats, shared by a concat buffer and its slots), this view's
+    channel offset in it, and whether every channel of this view has been summed by its producer."""
+    __slots__ = ("t", "g", "gw", "parent", "cs", "coff", "cs_ok", "kids")
 
-    def __init__(self, t: torch.Tensor, parent: Optional["Node"] = None):
+    def __init__(self, t: torch.Tensor, parent: Optional["Node"] = None, coff: int = 0):
         self.t = t
         self.g: Optional[torch.Tensor] = None
         self.gw = False          # gradient buffer holds valid data
         self.parent = parent
+        self.cs = None
+        self.coff = coff
+        self.cs_ok = False
+        self.kids: List["Node"] = []
+        if parent is not None:
+            parent.kids.append(self)
+
+    def colstats(self):
+        """(workspace, channel offset) for a producer's epilogue, or None when the images are too small
+        for the fused sums (the consumer then runs the statistics kernel)."""
+        if os.environ.get("FDX_NO_COLSTATS") or self.t.shape[1] * self.t.shape[2] < ops.COLSTATS_MIN_PIXELS:
+            return None
+        root = self.parent if self.parent is not None else self
+        if root.cs is None:
+            root.cs = ops.ColStats(root.t.shape[0], root.t.shape[-1], root.t.device)
+        self.cs_ok = True
+        return (root.cs, self.coff)
+
+    def stats(self, groups: int) -> torch.Tensor:
+        """GroupNorm statistics of this tensor: from the producers' epilogue sums when all of them
+        contributed, else one pass of fdx_groupnorm_stats."""
+        done = all(k.cs_ok for k in self.kids) if self.kids else self.cs_ok
+        root = self.parent if self.parent is not None else self
+        if done and root.cs is not None:
+            return ops.groupnorm_stats_from_cols(root.cs, groups, self.coff, self.t.shape[-1])
+        return ops.groupnorm_stats(self.t, groups)
 
     def grad_buf(self) -> torch.Tensor:
         if self.g is None:
@@ -300,7 +329,7 @@ class Unet:
             hh, ww = res_of_skip[k]
             buf = torch.empty((B, hh, ww, cx + ch_of_skip[k]), dtype=BF16, device=dev)
             parent = Node(buf)
-            cat_nodes[k] = (parent, Node(buf[..., :cx], parent), Node(buf[..., cx:], parent))
+            cat_nodes[k] = (parent, Node(buf[..., :cx], parent, 0), Node(buf[..., cx:], parent, cx))
 
         def new_node(hh, ww, c):
             return Node(torch.empty((B, hh, ww, c), dtype=BF16, device=dev))
@@ -352,7 +381,7 @@ class Unet:
                 h, w = h // 2, w // 2
                 dst = out_node(idx, h, w, cout)
                 ops.conv3x3_fwd(cur.t, W16[name + "/ConvLayer_0/conv/kernel"],
-                                W[name + "/ConvLayer_0/conv/bias"], out=dst.t, stride=2)
+                                W[name + "/ConvLayer_0/conv/bias"], out=dst.t, stride=2, colstats=dst.colstats())
                 tape.append(("down", name, cur, dst))
                 cur = dst
             elif kind == "up":
@@ -361,16 +390,18 @@ class Unet:
                 h, w = h * 2, w * 2
                 dst = out_node(idx, h, w, cout)
                 weff = ops.upconv3x3_pack(W[name + "/ConvLayer_0/conv/kernel"])
-                ops.upconv3x3_fwd(cur.t, weff, W[name + "/ConvLayer_0/conv/bias"], dst.t)
+                cs = dst.colstats() if cur.t.shape[1] * cur.t.shape[2] >= ops.COLSTATS_MIN_PIXELS else None
+                ops.upconv3x3_fwd(cur.t, weff, W[name + "/ConvLayer_0/conv/bias"], dst.t, colstats=cs)
                 tape.append(("up", name, cur, dst, weff if save else None))
                 cur = dst
             elif kind == "conv":
                 dst = out_node(idx, h, w, cout)
-                ops.conv3x3_fwd(cur.t, W16[name + "/conv/kernel"], W[name + "/conv/bias"], out=dst.t)
+                ops.conv3x3_fwd(cur.t, W16[name + "/conv/kernel"], W[name + "/conv/bias"], out=dst.t,
+                                colstats=dst.colstats())
                 tape.append(("conv", name, cur, dst))
                 cur = dst
             elif kind == "out":
-                st = ops.groupnorm_stats(cur.t, G)
+                st = cur.stats(G)
                 a = ops.groupnorm_apply(cur.t, G, st, W[self._nout + "/scale"], W[self._nout + "/bias"],
                                         OUT_EPS, True)
                 Fo = ops.conv_out_fwd(a, W[name + "/conv/kernel"], W[name + "/conv/bias"])
@@ -384,12 +415,14 @@ class Unet:
     def _res_fwd(self, name, xin: Node, dst: Node, emb16, W, W16, G, eps):
         x = xin.t
         cin, cout = x.shape[-1], dst.t.shape[-1]
-        st1 = ops.groupnorm_stats(x, G)
+        st1 = xin.stats(G)
         a1 = ops.groupnorm_apply(x, G, st1, W[f"{name}/{self._n1}/scale"], W[f"{name}/{self._n1}/bias"], eps, True)
         row = ops.linear_fwd(emb16, W16[f"{name}/temb_projection/kernel"],
                              bias=W[f"{name}/temb_projection/bias"], out_dtype=F32)
-        hmid = ops.conv3x3_fwd(a1, W16[f"{name}/conv1/conv/kernel"], W[f"{name}/conv1/conv/bias"], rowvec=row)
-        st2 = ops.groupnorm_stats(hmid, G)
+        hnode = Node(torch.empty((x.shape[0], x.shape[1], x.shape[2], cout), dtype=BF16, device=x.device))
+        hmid = ops.conv3x3_fwd(a1, W16[f"{name}/conv1/conv/kernel"], W[f"{name}/conv1/conv/bias"], rowvec=row,
+                               out=hnode.t, colstats=hnode.colstats())
+        st2 = hnode.stats(G)
         a2 = ops.groupnorm_apply(hmid, G, st2, W[f"{name}/{self._n2}/scale"], W[f"{name}/{self._n2}/bias"], eps, True)
         if cin != cout:
             Bn, hh, ww, _ = x.shape
@@ -398,7 +431,8 @@ class Unet:
                      x.stride(2), cout, cout, bias=W[f"{name}/residual_conv/conv/bias"])
         else:
             r = x
-        ops.conv3x3_fwd(a2, W16[f"{name}/conv2/conv/kernel"], W[f"{name}/conv2/conv/bias"], res=r, out=dst.t)
+        ops.conv3x3_fwd(a2, W16[f"{name}/conv2/conv/kernel"], W[f"{name}/conv2/conv/bias"], res=r, out=dst.t,
+                        colstats=dst.colstats())
         return ("res", name, xin, dst, st1, a1, hmid, st2, a2)
 
     @staticmethod

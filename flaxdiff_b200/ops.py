@@ -21,10 +21,39 @@ def _opt_act(t: Optional[torch.Tensor], name: str):
 
 
 # --------------------------------------------------------------------------- conv
+COLSTATS_SLOTS = 4
+COLSTATS_MIN_PIXELS = 128     # the fused epilogue sums need one image per 128-pixel output tile
+
+
+class ColStats:
+    """Per-(image, channel) sum / sum-of-squares workspace of one activation BUFFER, filled by the epilogues
+    of the convolutions that write into it (each at its channel offset) and turned into GroupNorm
+    statistics by groupnorm_stats_from_cols."""
+
+    def __init__(self, n: int, channels: int, device, slots: int = COLSTATS_SLOTS):
+        self.ws = torch.zeros((slots, n, 2, channels), dtype=torch.float32, device=device)
+        self.n, self.channels, self.slots = n, channels, slots
+
+    def desc(self, channel_offset: int = 0):
+        return _lib.fdx_colstats(self.ws.data_ptr() + 4 * channel_offset, self.slots, self.channels)
+
+
+def groupnorm_stats_from_cols(cs: ColStats, groups: int, c0: int = 0, channels: Optional[int] = None) -> torch.Tensor:
+    """fdx_groupnorm_stats' output for channels [c0, c0 + channels) of the buffer, from its epilogue sums."""
+    channels = cs.channels - c0 if channels is None else channels
+    stats = torch.empty((cs.n, groups, 2), dtype=torch.float32, device=cs.ws.device)
+    check(load().fdx_groupnorm_stats_from_cols(ptr(cs.ws), ctypes.c_int(cs.slots), ctypes.c_int(cs.n),
+                                               ctypes.c_int(cs.channels), ctypes.c_int(c0), ctypes.c_int(channels),
+                                               ctypes.c_int(groups), ptr(stats), stream_ptr()),
+          "groupnorm_stats_from_cols")
+    return stats
+
+
 def conv3x3_fwd(x: torch.Tensor, w_hwio: torch.Tensor, bias: Optional[torch.Tensor] = None,
                 rowvec: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None, stride: int = 1) -> torch.Tensor:
-    """3x3 SAME conv, NHWC bf16, HWIO bf16 weights; out = conv + bias + rowvec[n] + res."""
+                out: Optional[torch.Tensor] = None, stride: int = 1, colstats=None) -> torch.Tensor:
+    """3x3 SAME conv, NHWC bf16, HWIO bf16 weights; out = conv + bias + rowvec[n] + res.
+    colstats = (ColStats, channel offset): also accumulate the output's per-image channel sums."""
     n, h, w, cin = x.shape
     cout = w_hwio.shape[-1]
     assert w_hwio.dtype == torch.bfloat16 and w_hwio.is_contiguous()
@@ -32,6 +61,13 @@ def conv3x3_fwd(x: torch.Tensor, w_hwio: torch.Tensor, bias: Optional[torch.Tens
     ho, wo = (h + stride - 1) // stride, (w + stride - 1) // stride
     if out is None:
         out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
+    if colstats is not None:
+        d = colstats[0].desc(colstats[1])
+        check(load().fdx_conv3x3_fwd_stats(ctypes.byref(act(x, "x")), ptr(w_hwio), ptr(bias), ptr(rowvec),
+                                           _opt_act(res, "res"), ctypes.byref(act(out, "out")),
+                                           ctypes.c_int(stride), ctypes.byref(d), stream_ptr()),
+              "conv3x3_fwd_stats")
+        return out
     check(load().fdx_conv3x3_fwd(ctypes.byref(act(x, "x")), ptr(w_hwio), ptr(bias), ptr(rowvec),
                                  _opt_act(res, "res"), ctypes.byref(act(out, "out")),
                                  ctypes.c_int(stride), stream_ptr()), "conv3x3_fwd")
@@ -337,8 +373,15 @@ def upconv3x3_pack(w_hwio: torch.Tensor) -> torch.Tensor:
     return weff
 
 
-def upconv3x3_fwd(x: torch.Tensor, weff: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+def upconv3x3_fwd(x: torch.Tensor, weff: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
+                  colstats=None) -> torch.Tensor:
     """out[B,2h,2w,Cout] = conv3x3_SAME(nearest2x(x)) + bias, without the upsampled tensor."""
+    if colstats is not None:
+        d = colstats[0].desc(colstats[1])
+        check(load().fdx_upconv3x3_fwd_stats(ctypes.byref(act(x, "x")), ptr(weff), ptr(bias),
+                                             ctypes.byref(act(out, "out")), ctypes.byref(d), stream_ptr()),
+              "upconv3x3_fwd_stats")
+        return out
     check(load().fdx_upconv3x3_fwd(ctypes.byref(act(x, "x")), ptr(weff), ptr(bias), ctypes.byref(act(out, "out")),
                                    stream_ptr()), "upconv3x3_fwd")
     return out

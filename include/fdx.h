@@ -47,6 +47,22 @@ unsigned long long fdx_launch_count(void);
  * w_hwio is bf16.  Cin, Cout multiples of 64. */
 int fdx_conv3x3_fwd(const fdx_act* x, const void* w_hwio, const float* bias, const float* rowvec,
                     const fdx_act* res, const fdx_act* y, int stride, void* stream);
+/* Same convolution, additionally accumulating per (image, output channel) the sum and the sum of
+ * squares of the stored bf16 values - the statistics of the GroupNorm that consumes y
+ * (models/common.py:273-288), so that norm needs no pass of its own over y.
+ * cs->ws = f32 [slots][N][2][ld], zeroed by the caller, pre-offset to y's first channel inside the
+ * destination buffer (ld = that buffer's channel count).  FDX_ERR_UNSUPPORTED when an image of y has
+ * fewer than 128 pixels.  fdx_groupnorm_stats_from_cols turns the sums into fdx_groupnorm_stats' output. */
+typedef struct fdx_colstats {
+  float* ws;
+  int slots;
+  int ld;
+} fdx_colstats;
+int fdx_conv3x3_fwd_stats(const fdx_act* x, const void* w_hwio, const float* bias, const float* rowvec,
+                          const fdx_act* res, const fdx_act* y, int stride, const fdx_colstats* cs,
+                          void* stream);
+int fdx_groupnorm_stats_from_cols(const float* cols, int slots, int N, int ld, int c0, int C, int groups,
+                                  float* stats, void* stream);   /* channels [c0, c0+C) of the ld-wide rows */
 /* d(loss)/dx of the conv above (jax.value_and_grad, trainer/general_diffusion_trainer.py:321). */
 int fdx_conv3x3_dgrad(const fdx_act* dy, const void* w_hwio, const fdx_act* dx, int stride,
                       int accumulate, void* stream);
@@ -85,6 +101,8 @@ int fdx_gemm(const fdx_gemm_desc* g, void* stream);
 int fdx_upconv3x3_pack(const float* w_hwio, int cin, int cout, void* weff_bf16, void* stream);
 int fdx_upconv3x3_fwd(const fdx_act* x, const void* weff_bf16, const float* bias, const fdx_act* y,
                       void* stream);
+int fdx_upconv3x3_fwd_stats(const fdx_act* x, const void* weff_bf16, const float* bias, const fdx_act* y,
+                            const fdx_colstats* cs, void* stream);   /* cs as in fdx_conv3x3_fwd_stats */
 int fdx_upconv3x3_dgrad(const fdx_act* dy, const void* weff_bf16, const fdx_act* dx, int accumulate,
                         void* stream);
 int fdx_upconv3x3_wgrad(const fdx_act* x, const fdx_act* dy, float* dweff_ws, float* dw_hwio,
