@@ -72,5 +72,9 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream);
 // All-nine-taps weight-gradient kernel (fdx_wgrad9.cu); FDX_ERR_UNSUPPORTED = shape not covered.
 int fdx_wgrad9_launch(const fdx_act* x, const fdx_act* dy, float* dw, cudaStream_t stream);
 
+// Transposed formulation (weights as A, 256 pixels as N) for Ncols = 64 / 128 (fdx_tct.cu);
+// FDX_ERR_UNSUPPORTED = geometry not covered.
+int fdx_tct_launch(const TcLaunch& L, cudaStream_t stream);
+
 // Halo-sharing 3x3 stride-1 kernel (fdx_conv3.cu); FDX_ERR_UNSUPPORTED = geometry not covered.
 int fdx_conv3_launch(const TcLaunch& L, int BN, cudaStream_t stream);
