@@ -546,15 +546,10 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
   FDX_REQUIRE(L.A.strides[0] == 1 && L.B.strides[0] == 1, "tc: innermost strides must be 1");
 
   // Few output columns (Ncols = 64 / 128): the transposed formulation (fdx_tct.cu) issues M x 256 x 16 MMAs
-  // instead of 128 x Ncols x 16 ones.  Measured per layer (profiles/layers_r01_tct.txt): always faster for
-  // the data gradient and for Ncols = 128; at Ncols = 64 the forward (bias + timestep row + residual +
-  // GroupNorm sums in an epilogue that has 16 live lanes per warp) only wins from K = 128 up.
+  // instead of 128 x Ncols x 16 ones; faster on every such layer (profiles/layers_r01_tct.txt).
   if (L.mode != TC_MNMN && !getenv("FDX_NO_TCT")) {
-    const bool fwd = (L.mode == TC_KMN);
-    if (!(fwd && L.Ncols == 64 && L.K < 128)) {
-      const int rt = fdx_tct_launch(L, stream);
-      if (rt != FDX_ERR_UNSUPPORTED) return rt;
-    }
+    const int rt = fdx_tct_launch(L, stream);
+    if (rt != FDX_ERR_UNSUPPORTED) return rt;
   }
   TcDev d{};
   d.mode = L.mode;

@@ -11,6 +11,12 @@
 // channel, column = pixel; the epilogue warps therefore own whole channels (bias and the fused per-channel
 // GroupNorm sums are per-thread scalars) and write 64-byte channel runs per pixel.
 //
+// M = 64 (64 output channels): an M = 64 accumulator occupies lanes 0-15 of every TMEM sub-partition only,
+// so TWO pixel halves (2 x 256 pixels, 16 wide x 32 tall) are interleaved into the same 256 columns - half
+// 0 in lanes 0-15, half 1 in lanes 16-31 (TMEM lane offset 16 of the MMA's D address) - and the epilogue
+// warps again work with all 32 lanes.  K steps alternate between the halves; the 8 KB weight tile is
+// simply fetched for both.
+//
 // Same barrier topology as fdx_tc.cu: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue,
 // double-buffered 2 x 256-column TMEM accumulator.  Geometry: stride 1, W and H multiples of 16.
 #include "fdx_tc.cuh"
@@ -43,6 +49,9 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   constexpr int kWBytes = MT * 128;                       // MT channels x 64 k
   constexpr int kStageBytes = kWBytes + kPixBytes;
   constexpr int S = (MT == 128) ? 4 : 5;
+  constexpr bool IL = (MT == 64);                         // two interleaved pixel halves per tile
+  constexpr int NH = IL ? 2 : 1;
+  constexpr int TH = 16 * NH;                             // pixel rows per tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -76,8 +85,9 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         const int cb = tile % p.cblks;
         const int mt = tile / p.cblks;
         const int xb = mt % p.nxb, yb = (mt / p.nxb) % p.nyb, nb = mt / (p.nxb * p.nyb);
-        const int x0 = xb * 16, y0 = yb * 16;
-        for (int q = 0; q < nk; ++q) {
+        const int x0 = xb * 16;
+        for (int qq = 0; qq < nk * NH; ++qq) {
+          const int q = qq / NH, y0 = yb * TH + 16 * (qq % NH);
           const int t = q / p.kchunks, kc = q % p.kchunks;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sw = smem + stage * kStageBytes;
@@ -106,7 +116,9 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-        for (int q = 0; q < nk; ++q) {
+        for (int qq = 0; qq < nk * NH; ++qq) {
+          const int q = qq / NH;
+          const uint32_t dh = d_tmem + ((uint32_t)((qq % NH) * 16) << 16);   // half 1 -> TMEM lanes 16..31
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sw = smem_u32(smem + stage * kStageBytes);
@@ -116,7 +128,7 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             const uint64_t da = A_MN ? umma_desc_sw128(sw + k * 2048, 8192, 1024)
                                      : umma_desc_sw128(sw + k * 32, 16, 1024);
             const uint64_t db = umma_desc_sw128(sx + k * 32, 16, 1024);
-            umma_f16(d_tmem, da, db, idesc, (q | k) != 0 ? 1u : 0u);
+            umma_f16(dh, da, db, idesc, (q | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -133,10 +145,11 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     // (pixel l / PPX + k * (32 / PPX), piece l % PPX).  A lane always owns the same 8 channels, so the
     // fused GroupNorm sums are per-lane registers, reduced once per tile.
     const int q = warp & 3;
-    constexpr int CW = (MT == 128) ? 32 : 16;          // channels held by one warp
-    constexpr int PPX = CW / 8;                          // 16-byte pieces per pixel per warp (4 or 2)
-    const bool lane_live = (MT == 128) || (lane < 16);
-    const int crow = (MT == 128) ? q * 32 + lane : q * 16 + (lane & 15);
+    constexpr int CW = 32;                               // staging slots per pixel column = lanes of the warp:
+                                                         // M=128: 32 channels; M=64: 16 channels x 2 halves
+    constexpr int PPX = 4;                               // 16-byte pieces per staged pixel column
+    constexpr int CPW = IL ? 16 : 32;                    // channels owned by one warp
+    const int crow = IL ? q * 16 + (lane & 15) : q * 32 + lane;
     constexpr int RS = CW + 4;                           // padded row (floats): conflict-free 16-byte reads
     float* stg = reinterpret_cast<float*>(smem + S * kStageBytes + 256) + q * (32 * RS);   // [32 px][RS] f32
     const int piece = lane % PPX, prow = lane / PPX;     // read phase: this lane's piece and first pixel
@@ -148,18 +161,20 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       const int mt = tile / p.cblks;
       const int xb = mt % p.nxb, yb = (mt / p.nxb) % p.nyb, nb = mt / (p.nxb * p.nyb);
       const int co = cb * MT + crow;                      // write phase: this thread's channel
-      const int cw0 = cb * MT + q * CW;                   // first channel of this warp
-      const bool live = lane_live && co < p.Ncols;
-      const long long obase = (long long)nb * p.os_n + (long long)(yb * 16) * p.os_y + (long long)(xb * 16) * p.os_x;
-      const long long rbase = (long long)nb * p.rs_n + (long long)(yb * 16) * p.rs_y + (long long)(xb * 16) * p.rs_x;
+      const int cw0 = cb * MT + q * CPW;                  // first channel of this warp
+      const bool live = co < p.Ncols;
+      // read phase: piece -> (pixel half, 8-channel group); half 1 lies 16 pixel rows below half 0
+      const int yh = yb * TH + (IL ? 16 * (piece >> 1) : 0);
+      const long long obase = (long long)nb * p.os_n + (long long)yh * p.os_y + (long long)(xb * 16) * p.os_x;
+      const long long rbase = (long long)nb * p.rs_n + (long long)yh * p.rs_y + (long long)(xb * 16) * p.rs_x;
       float add = 0.f;
       if (live) {
         if (p.bias) add += __ldg(p.bias + co);
         if (p.rowvec) add += __ldg(p.rowvec + (long long)nb * p.Ncols + co);
       }
       // residual pieces are requested one 32-pixel chunk ahead (the first before the accumulator wait)
-      const int ch = cw0 + piece * 8;                     // read phase: this lane's first channel
-      const bool ch_ok = ch < p.Ncols;
+      const int ch = cw0 + (IL ? (piece & 1) : piece) * 8;   // read phase: this lane's first channel
+      const bool ch_ok = ch < p.Ncols && yh < p.H;           // (H % 32 == 16: the last tile has no half 1)
       auto load_res = [&](int c0, uint4 (&r)[PPX]) {
 #pragma unroll
         for (int k = 0; k < PPX; ++k) {
@@ -184,11 +199,8 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         tmem_ld_32x32(t_addr + c0, v);
         tmem_ld_wait();
         // ---- write phase: stg[px j][channel (lane within the warp's CW)] ----
-        if (lane_live) {
-          const int cl = (MT == 128) ? lane : (lane & 15);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg[j * RS + cl] = __uint_as_float(v[j]) * p.alpha + add;
-        }
+        for (int j = 0; j < 32; ++j) stg[j * RS + lane] = __uint_as_float(v[j]) * p.alpha + add;
         __syncwarp();
         load_res(c0 + 32, rnxt);
         // ---- read phase: 16-byte channel pieces; columns c0 .. c0+31 = pixel rows c0/16, c0/16 + 1 ----
@@ -229,12 +241,12 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
 #pragma unroll
-          for (int o = PPX; o < 32; o <<= 1) {
+          for (int o = (IL ? 2 : PPX); o < 32; o <<= 1) {
             s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], o);
             s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
           }
         }
-        if (lane < PPX && ch_ok) {
+        if (lane < (IL ? 2 : PPX) && ch < p.Ncols) {
           float* w = p.cs_ws + (((long long)(tile % p.cs_slots) * p.nimg + nb) * 2) * p.cs_ld + ch;
 #pragma unroll
           for (int i = 0; i < 8; ++i) { atomicAdd(w + i, s0[i]); atomicAdd(w + p.cs_ld + i, s1[i]); }
@@ -278,11 +290,11 @@ int fdx_tct_launch(const TcLaunch& L, cudaStream_t stream) {
   if (L.W % 16 != 0 || L.H % 16 != 0 || L.K % 64 != 0) return FDX_ERR_UNSUPPORTED;
   TctDev d{};
   d.W = L.W; d.H = L.H; d.nimg = L.N;
-  d.nxb = L.W / 16; d.nyb = L.H / 16;
+  const int MT = (L.Ncols % 128 == 0) ? 128 : 64;
+  d.nxb = L.W / 16; d.nyb = (MT == 64) ? (L.H + 31) / 32 : L.H / 16;
   d.ntaps = L.ntaps;
   for (int i = 0; i < kTcMaxTaps; ++i) { d.tap_dx[i] = L.tap_dx[i]; d.tap_dy[i] = L.tap_dy[i]; d.tap_b[i] = L.tap_b[i]; }
   d.K = L.K; d.kchunks = L.K / 64; d.Ncols = L.Ncols;
-  const int MT = (L.Ncols % 128 == 0) ? 128 : 64;
   d.cblks = L.Ncols / MT;
   d.ntiles = d.cblks * d.nxb * d.nyb * d.nimg;
   d.out = L.out; d.os_x = L.os_x; d.os_y = L.os_y; d.os_n = L.os_n;

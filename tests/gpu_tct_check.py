@@ -1,4 +1,4 @@
-"""Transposed small-Cout kernels (FDX_TCT=1, fdx_tct.cu) against the generic engine on full-size layers:
+"""Transposed small-Cout kernels (fdx_tct.cu; baseline = FDX_NO_TCT=1) against the generic engine on full-size layers:
 outputs must agree to bf16 rounding (same products, different summation order), plus per-layer timing.
     python tests/gpu_tct_check.py [res] [batch]
 """
@@ -49,9 +49,9 @@ def main():
         outs, times, stats = [], [], []
         for tct in (False, True):
             if tct:
-                os.environ["FDX_TCT"] = "1"
+                os.environ.pop("FDX_NO_TCT", None)
             else:
-                os.environ.pop("FDX_TCT", None)
+                os.environ["FDX_NO_TCT"] = "1"
             y = torch.empty(B, h, h, cout, device=dev, dtype=torch.bfloat16)
             dx = torch.empty_like(x)
             cs = ops.ColStats(B, cout, dev)
