@@ -493,7 +493,8 @@ def profile_tc(trainer, images, noise, t):
     """CUDA-event time of every tcgen05 engine launch (conv3x3 fwd/dgrad/wgrad, gemm) in one eager step."""
     import torch
     from flaxdiff_b200 import ops
-    names = ["conv3x3_fwd", "conv3x3_dgrad", "conv3x3_wgrad", "gemm"]
+    names = ["conv3x3_fwd", "conv3x3_dgrad", "conv3x3_wgrad", "gemm", "upconv3x3_fwd", "upconv3x3_dgrad",
+             "upconv3x3_wgrad"]
     orig = {n: getattr(ops, n) for n in names}
     events = []
 
@@ -506,6 +507,10 @@ def profile_tc(trainer, images, noise, t):
             events.append((s, e))
             return r
         return inner
+    # one stream, no micro-batch / side-stream overlap: a kernel's duration is only meaningful when it runs alone
+    saved_env = {k: os.environ.get(k) for k in ("FDX_MICROBATCH", "FDX_NO_SIDE")}
+    os.environ["FDX_MICROBATCH"] = "1"
+    os.environ["FDX_NO_SIDE"] = "1"
     try:
         for n in names:
             setattr(ops, n, wrap(orig[n]))
@@ -514,6 +519,11 @@ def profile_tc(trainer, images, noise, t):
     finally:
         for n in names:
             setattr(ops, n, orig[n])
+        for k, v in saved_env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     return sum(s.elapsed_time(e) for s, e in events), len(events)
 
 

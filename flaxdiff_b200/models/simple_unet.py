@@ -43,6 +43,34 @@ OUT_EPS = 1e-6      # flax GroupNorm default epsilon for Unet.conv_out_norm (sim
 ATTN_EPS = 1e-4     # TransformerBlock.norm_epsilon, models/attention.py:319
 
 
+class _SideStream:
+    """Weight-gradient kernels have no consumer before the optimizer step, so the backward pass issues them
+    on a second stream: the HBM-bound GroupNorm-backward kernels of the main (data-gradient) chain then
+    share the SMs with the tensor-core-bound weight-gradient kernels instead of running after them.
+    Tensors handed to `run` are kept alive until `join` (the caching allocator must not recycle them while
+    the side stream still reads them).  Works inside CUDA-graph capture (event fork / wait_stream join)."""
+
+    def __init__(self, enabled: bool):
+        self.stream = torch.cuda.Stream() if enabled else None
+        self.keep: List[torch.Tensor] = []
+
+    def run(self, fn, *tensors):
+        if self.stream is None:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.extend(tensors)
+
+    def join(self):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.keep.clear()
+
+
 class Node:
     """An activation view plus (lazily) its gradient view.  `cs` / `coff` / `cs_ok`: the buffer's
     per-image channel-sum workspace (ops.ColStats, shared by a concat buffer and its slots), this view's
@@ -496,6 +524,7 @@ class Unet:
         B = saved["B"]
         dev = dF.device
         demb = torch.zeros((B, self.emb_features), dtype=F32, device=dev)
+        side = _SideStream(not os.environ.get("FDX_NO_SIDE"))
 
         def want(node: Node):
             """(grad buffer, accumulate?) for a consumer adding into node's gradient."""
@@ -540,12 +569,13 @@ class Unet:
                 da = torch.empty_like(a)
                 col = ops.im2col3(dF, -1, False)          # shared by the data and weight gradients
                 ops.conv_out_dgrad(dF, W[name + "/conv/kernel"], da, col=col)
-                ops.conv_out_wgrad(a, dF, Gd[name + "/conv/kernel"], Gd[name + "/conv/bias"], col=col)
+                side.run(lambda: ops.conv_out_wgrad(a, dF, Gd[name + "/conv/kernel"], Gd[name + "/conv/bias"], col=col),
+                         col)
                 dx, acc = want(xin)
                 ops.groupnorm_bwd(xin.t, da, G, st, W[self._nout + "/scale"], W[self._nout + "/bias"], OUT_EPS,
                                   True, Gd[self._nout + "/scale"], Gd[self._nout + "/bias"], dx, acc)
             elif kind == "res":
-                self._res_bwd(rec, W, W16, Gd, G, emb16, demb, want, grad_of)
+                self._res_bwd(rec, W, W16, Gd, G, emb16, demb, want, grad_of, side)
                 xin = rec[2]
                 if id(xin) in children:
                     mark_children_written(xin, children[id(xin)])
@@ -554,16 +584,16 @@ class Unet:
             elif kind == "conv":
                 _, _, xin, dst = rec
                 dy = grad_of(dst)
-                ops.conv3x3_wgrad(xin.t, dy, Gd[name + "/conv/kernel"])
-                ops.colsum(dy, False, out=Gd[name + "/conv/bias"])
+                side.run(lambda: (ops.conv3x3_wgrad(xin.t, dy, Gd[name + "/conv/kernel"]),
+                                  ops.colsum(dy, False, out=Gd[name + "/conv/bias"])))
                 dx, acc = want(xin)
                 ops.conv3x3_dgrad(dy, W16[name + "/conv/kernel"], dx, accumulate=acc)
             elif kind == "down":
                 _, _, xin, dst = rec
                 dy = grad_of(dst)
                 kn = name + "/ConvLayer_0/conv/"
-                ops.conv3x3_wgrad(xin.t, dy, Gd[kn + "kernel"], stride=2)
-                ops.colsum(dy, False, out=Gd[kn + "bias"])
+                side.run(lambda: (ops.conv3x3_wgrad(xin.t, dy, Gd[kn + "kernel"], stride=2),
+                                  ops.colsum(dy, False, out=Gd[kn + "bias"])))
                 dx, acc = want(xin)
                 ops.conv3x3_dgrad(dy, W16[kn + "kernel"], dx, stride=2, accumulate=acc)
             elif kind == "up":
@@ -572,20 +602,21 @@ class Unet:
                 kn = name + "/ConvLayer_0/conv/"
                 if weff is None:
                     weff = ops.upconv3x3_pack(W[kn + "kernel"])
-                ops.upconv3x3_wgrad(xin.t, dy, Gd[kn + "kernel"])
-                ops.colsum(dy, False, out=Gd[kn + "bias"])
+                side.run(lambda: (ops.upconv3x3_wgrad(xin.t, dy, Gd[kn + "kernel"]),
+                                  ops.colsum(dy, False, out=Gd[kn + "bias"])))
                 dx, acc = want(xin)
                 ops.upconv3x3_dgrad(dy, weff, dx, accumulate=acc)
             elif kind == "conv_in":
                 _, _, x_bf16, dst = rec
                 dy = grad_of(dst)
-                ops.conv_in_wgrad(x_bf16, dy, Gd[name + "/conv/kernel"], Gd[name + "/conv/bias"])
+                side.run(lambda: ops.conv_in_wgrad(x_bf16, dy, Gd[name + "/conv/kernel"], Gd[name + "/conv/bias"]))
+        side.join()
         # timestep-embedding MLP
         tp = "TimeProjection_0/DenseGeneral_"
         ops.time_embed_bwd(demb, saved["temb_saved"], W[tp + "1/kernel"], Gd[tp + "0/kernel"], Gd[tp + "0/bias"],
                            Gd[tp + "1/kernel"], Gd[tp + "1/bias"])
 
-    def _res_bwd(self, rec, W, W16, Gd, G, emb16, demb, want, grad_of):
+    def _res_bwd(self, rec, W, W16, Gd, G, emb16, demb, want, grad_of, side):
         _, name, xin, dst, st1, a1, hmid, st2, a2 = rec
         x = xin.t
         cin, cout = x.shape[-1], dst.t.shape[-1]
@@ -593,8 +624,17 @@ class Unet:
         Bn, hh, ww, _ = x.shape
         E = emb16.shape[1]
         # conv2
-        ops.conv3x3_wgrad(a2, dout, Gd[f"{name}/conv2/conv/kernel"])
-        ops.colsum(dout, False, out=Gd[f"{name}/conv2/conv/bias"])
+        kres = f"{name}/residual_conv/conv/"
+        M = Bn * hh * ww
+
+        def conv2_param_grads():
+            ops.conv3x3_wgrad(a2, dout, Gd[f"{name}/conv2/conv/kernel"])
+            ops.colsum(dout, False, out=Gd[f"{name}/conv2/conv/bias"])
+            if cin != cout:      # the 1x1 residual conv sees the same dout
+                ops.gemm(GEMM_MNMN, x, dout, Gd[kres + "kernel"], cin, cout, M, x.stride(2), dout.stride(2), cout,
+                         atomic=True, reduce_batch=True)
+                Gd[kres + "bias"].copy_(Gd[f"{name}/conv2/conv/bias"])
+        side.run(conv2_param_grads)
         # conv2 data gradient -> norm2 + silu backward (first pass fused into the dgrad epilogue).
         # The same pass also emits the per-image / total column sums of dh: the timestep
         # row-vector gradient and the conv1 (= temb_projection) bias gradient
@@ -604,14 +644,18 @@ class Unet:
                                      W[f"{name}/{self._n2}/scale"], W[f"{name}/{self._n2}/bias"], RES_EPS,
                                      Gd[f"{name}/{self._n2}/scale"], Gd[f"{name}/{self._n2}/bias"], dh, False,
                                      csum_img=drow, csum_tot=Gd[f"{name}/conv1/conv/bias"])
-        Gd[f"{name}/temb_projection/bias"].copy_(Gd[f"{name}/conv1/conv/bias"])
-        drow16 = ops.cast_f32_bf16(drow)
-        ops.gemm(GEMM_MNMN, emb16, drow16, Gd[f"{name}/temb_projection/kernel"], E, cout, Bn, E, cout, cout,
-                 atomic=True, reduce_batch=True)
-        ops.gemm(GEMM_KK, drow16, W16[f"{name}/temb_projection/kernel"], demb, Bn, E, cout, cout, cout, E,
-                 atomic=True)
-        # conv1
-        ops.conv3x3_wgrad(a1, dh, Gd[f"{name}/conv1/conv/kernel"])
+
+        def conv1_param_grads():
+            # timestep projection (its bias gradient = conv1's), then the conv1 weight gradient
+            Gd[f"{name}/temb_projection/bias"].copy_(Gd[f"{name}/conv1/conv/bias"])
+            drow16 = ops.cast_f32_bf16(drow)
+            ops.gemm(GEMM_MNMN, emb16, drow16, Gd[f"{name}/temb_projection/kernel"], E, cout, Bn, E, cout, cout,
+                     atomic=True, reduce_batch=True)
+            ops.gemm(GEMM_KK, drow16, W16[f"{name}/temb_projection/kernel"], demb, Bn, E, cout, cout, cout, E,
+                     atomic=True)
+            side.keep.append(drow16)
+            ops.conv3x3_wgrad(a1, dh, Gd[f"{name}/conv1/conv/kernel"])
+        side.run(conv1_param_grads, dh, drow)
         # conv1 data gradient -> norm1 + silu backward -> dx
         dx, acc = want(xin)
         ops.conv_dgrad_groupnorm_bwd(dh, W16[f"{name}/conv1/conv/kernel"], x, G, st1,
@@ -620,12 +664,7 @@ class Unet:
         del dh
         # residual path
         if cin != cout:
-            kn = f"{name}/residual_conv/conv/"
-            M = Bn * hh * ww
-            ops.gemm(GEMM_MNMN, x, dout, Gd[kn + "kernel"], cin, cout, M, x.stride(2), dout.stride(2), cout,
-                     atomic=True, reduce_batch=True)
-            Gd[kn + "bias"].copy_(Gd[f"{name}/conv2/conv/bias"])
-            ops.gemm(GEMM_KK, dout, W16[kn + "kernel"].view(cin, cout), dx, M, cin, cout, dout.stride(2), cout,
+            ops.gemm(GEMM_KK, dout, W16[kres + "kernel"].view(cin, cout), dx, M, cin, cout, dout.stride(2), cout,
                      dx.stride(2), res=dx, r_ld=dx.stride(2))
         else:
             ops.act_add(dx, dout, dx)

@@ -197,7 +197,45 @@ class GeneralDiffusionTrainer:
 
     # ------------------------------------------------------------------ the step
     def _fwd_bwd(self, images, noise, noise_level, ctx=None):
-        """noise-add -> UNet fwd -> loss -> UNet bwd; returns the loss tensor (f32[1])."""
+        """noise-add -> UNet fwd -> loss -> UNet bwd; returns the loss tensor (f32[1]); gradients land in
+        self._grads.  FDX_MICROBATCH=2 processes the batch as two micro-batches on two streams (the sum of
+        the two mean-loss gradients, halved, is the full-batch gradient: GroupNorm is per sample) so that
+        the HBM-bound kernels of one half overlap the tensor-core kernels of the other; measured slower
+        than one batch with side-stream weight gradients (24.2 vs 22.3 ms/step at C2), hence opt-in."""
+        B = images.shape[0]
+        nmb = int(os.environ.get("FDX_MICROBATCH", "1"))
+        if nmb < 2 or B % nmb != 0 or B // nmb < 2:
+            return self._fwd_bwd_one(images, noise, noise_level, ctx, self._grads)
+        if getattr(self, "_mb_grads", None) is None or len(self._mb_grads) != nmb:
+            self._mb_grads = [self.state.params.zeros_like() for _ in range(nmb)]
+            self._mb_streams = [torch.cuda.Stream() for _ in range(nmb)]
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        losses = []
+        step = B // nmb
+        for h in range(nmb):
+            sl = slice(h * step, (h + 1) * step)
+            self._mb_streams[h].wait_event(ev)
+            with torch.cuda.stream(self._mb_streams[h]):
+                losses.append(self._fwd_bwd_one(images[sl], noise[sl], noise_level[sl],
+                                                None if ctx is None else ctx[sl], self._mb_grads[h]))
+        for h in range(nmb):
+            main.wait_stream(self._mb_streams[h])
+        g = self._grads.flat
+        if nmb == 2:
+            torch.lerp(self._mb_grads[0].flat, self._mb_grads[1].flat, 0.5, out=g)
+        else:
+            torch.add(self._mb_grads[0].flat, self._mb_grads[1].flat, out=g)
+            for h in range(2, nmb):
+                g.add_(self._mb_grads[h].flat)
+            g.mul_(1.0 / nmb)
+        loss = losses[0]
+        for h in range(1, nmb):
+            loss = loss + losses[h]
+        return loss / nmb
+
+    def _fwd_bwd_one(self, images, noise, noise_level, ctx, grads):
         sched, tr, st = self.noise_schedule, self.model_output_transform, self.state
         B = images.shape[0]
         rates = sched.get_rates(noise_level, shape=(-1,))
@@ -210,8 +248,8 @@ class GeneralDiffusionTrainer:
         x_t, target, model_in = ops.diffuse_forward(images, noise, alpha, sigma, c_in, True, tr.target_kind)
         F, saved = self.model.forward(st.params, model_in, t_model, ctx, save=True)
         loss, dF = ops.loss_fwd_bwd(F, x_t, target, c_out, c_skip, weight, want_grad=True)
-        self._grads.flat.zero_()
-        self.model.backward(st.params, saved, dF, self._grads)
+        grads.flat.zero_()
+        self.model.backward(st.params, saved, dF, grads)
         return loss
 
     def _define_train_step(self, batch_size=None):
