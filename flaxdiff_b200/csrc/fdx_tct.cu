@@ -286,7 +286,8 @@ int launch_tct(const CUtensorMap& mW, const CUtensorMap& mX, const TctDev& d, cu
 int fdx_tct_launch(const TcLaunch& L, cudaStream_t stream) {
   if (L.mode == TC_MNMN || L.gemm_like || L.es != 1 || L.out_f32 || L.out_atomic || L.gn_ab || L.b_batched)
     return FDX_ERR_UNSUPPORTED;
-  if (L.Ncols != 64 && L.Ncols != 128) return FDX_ERR_UNSUPPORTED;
+  // column counts the generic engine would have to cover with N < 256 tiles (64, 128, 192, 320, 384, ...)
+  if (L.Ncols % 64 != 0 || L.Ncols % 256 == 0 || L.Ncols > 512) return FDX_ERR_UNSUPPORTED;
   if (L.W % 16 != 0 || L.H % 16 != 0 || L.K % 64 != 0) return FDX_ERR_UNSUPPORTED;
   TctDev d{};
   d.W = L.W; d.H = L.H; d.nimg = L.N;

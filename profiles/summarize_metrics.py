@@ -43,9 +43,9 @@ tc_bytes = tc_ns = 0.0
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     gb = (a[2] + a[3]) / 1e9
     print(f"{k[:44]:44s} {a[0]:4d} {a[1] / 1e6:8.3f} {100 * a[1] / tot:5.1f}% {gb:8.2f} {gb / (a[1] / 1e9):7.0f} {a[4] / a[1]:7.1f}")
-    if k.startswith('fdx_tc_kernel') or k.startswith('fdx_wgrad9'):
+    if k.startswith('fdx_tc_kernel') or k.startswith('fdx_tct_kernel') or k.startswith('fdx_wgrad9'):
         tc_bytes += a[2] + a[3]
         tc_ns += a[1]
-print(f"tensor-core engine (fdx_tc_kernel + fdx_wgrad9): {tc_ns / 1e6:.2f} ms, {tc_bytes / 1e9:.2f} GB DRAM traffic per step")
+print(f"tensor-core engine (fdx_tc_kernel + fdx_tct_kernel + fdx_wgrad9): {tc_ns / 1e6:.2f} ms, {tc_bytes / 1e9:.2f} GB DRAM traffic per step")
 if len(sys.argv) > 3 and sys.argv[2] == '--json':
     print(json.dumps({sys.argv[3]: {"dram_bytes_per_step": tc_bytes, "source": sys.argv[1]}}))

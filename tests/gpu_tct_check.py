@@ -13,7 +13,7 @@ from flaxdiff_b200 import ops  # noqa: E402
 dev = torch.device("cuda")
 # (res divisor, Cin, Cout): forward needs Cout in {64,128}; dgrad needs Cin in {64,128}
 SHAPES = [(1, 64, 64), (1, 128, 64), (1, 320, 64), (2, 128, 128), (2, 192, 128), (2, 576, 128), (2, 64, 128),
-          (4, 128, 128), (1, 64, 128)]
+          (4, 128, 128), (1, 64, 128), (2, 128, 192), (4, 384, 256), (1, 64, 320)]
 
 
 def timeit(fn, iters=10):
