@@ -28,6 +28,12 @@ def edm_train_step(P, opt_state, images_u8, noise, t, freqs, attention_configs=(
     pred = c_out * F + c_skip * x_t
     w = (s4 ** 2 + sd ** 2) / ((s4 * sd) ** 2 + 1e-6)
     loss = (0.5 * (pred - data) ** 2 * w).mean()
+    _adamw_ema_update(P, opt_state, loss, lr, wd, ema, ema_decay, step)
+    return loss.detach()
+
+
+def _adamw_ema_update(P, opt_state, loss, lr, wd, ema, ema_decay, step):
+    """optax.adamw (training.py:598-608) then apply_ema (trainer/diffusion_trainer.py:31-37), in place."""
     grads = torch.autograd.grad(loss, list(P.values()))
     b1, b2, eps = 0.9, 0.999, 1e-8
     with torch.no_grad():
@@ -39,6 +45,25 @@ def edm_train_step(P, opt_state, images_u8, noise, t, freqs, attention_configs=(
             p.sub_(lr * (mh / (vh.sqrt() + eps) + wd * p))
             if ema is not None:
                 ema[k].mul_(ema_decay).add_(p, alpha=1 - ema_decay)
+
+
+def ddpm_train_step(P, opt_state, images_u8, noise, t_int, freqs, attention_configs=(None,) * 4,
+                    timesteps=1000, lr=2.7e-4, wd=1e-4, ema=None, ema_decay=0.999, step=1):
+    """BASELINE configs[0]: LinearNoiseSchedule(1000) + EpsilonPredictionTransform training step
+    (general_diffusion_trainer.py:285-302 with schedulers/discrete.py:47-57 and predictors/__init__.py:19-44):
+    x_t = sqrt(acp[t]) x0 + sqrt(1-acp[t]) eps, the model sees (x_t, t) unscaled, target = eps,
+    loss = mean(0.5 (pred - eps)^2 * p2_weight[t])."""
+    from . import diffusion_ref as R
+    data = (images_u8.to(torch.float32) - 127.5) / 127.5
+    T = R.linear_tables(timesteps)
+    idx = R.discrete_index(t_int.numpy(), timesteps)
+    a = torch.from_numpy(T["sqrt_alpha_cumprod"][idx]).view(-1, 1, 1, 1)
+    sg = torch.from_numpy(T["sqrt_one_minus_alpha_cumprod"][idx]).view(-1, 1, 1, 1)
+    w = torch.from_numpy(T["p2_loss_weights"][idx]).view(-1, 1, 1, 1)
+    x_t = a * data + sg * noise
+    pred = unet_ref.unet_forward(P, x_t, t_int.to(torch.float32), freqs, attention_configs=attention_configs)
+    loss = (0.5 * (pred - noise) ** 2 * w).mean()
+    _adamw_ema_update(P, opt_state, loss, lr, wd, ema, ema_decay, step)
     return loss.detach()
 
 

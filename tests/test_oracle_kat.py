@@ -56,3 +56,25 @@ def test_euler_step_on_ve_schedule():
     cs, r = np.float32(3.0), np.float32(0.25)
     out = R.euler_step(x, x0, [1, 1], [cs, cs], [1, 1], [cs * r, cs * r])
     np.testing.assert_allclose(out, x0 + r * (x - x0), rtol=2e-5, atol=2e-6)
+
+
+def test_oracle_ddpm_train_step_configs0():
+    """BASELINE configs[0] on the CPU oracle: LinearNoiseSchedule + epsilon prediction.  At t = 0 the input is
+    almost the clean image and the p2 weight (1 + acp/(1-acp))^-1 = 1 - acp = beta_0 = 1e-4 nearly cancels the loss."""
+    import torch
+    from oracle import train_ref, unet_ref  # noqa: F401
+    from flaxdiff_b200 import utils
+    from flaxdiff_b200.models.simple_unet import Unet
+    torch.manual_seed(0)
+    model = Unet(attention_configs=(None,) * 4)
+    fp = model.init(utils.PRNGKey(4), device=torch.device("cpu"))
+    P = {k: v.clone().requires_grad_(True) for k, v in fp.named.items()}
+    freqs = model._fourier_freqs("cpu")
+    img = torch.randint(0, 256, (2, 8, 8, 3), dtype=torch.uint8)
+    noise = torch.randn(2, 8, 8, 3)
+    before = {k: v.detach().clone() for k, v in P.items()}
+    l_hi = train_ref.ddpm_train_step(P, {}, img, noise, torch.tensor([999, 500]), freqs, lr=1e-3)
+    assert torch.isfinite(l_hi) and l_hi > 0
+    assert any(not torch.equal(before[k], P[k].detach()) for k in P)          # AdamW moved the parameters
+    l_lo = train_ref.ddpm_train_step(P, {}, img, noise, torch.tensor([0, 0]), freqs, lr=0.0, wd=0.0)
+    assert l_lo < 1e-3 * l_hi

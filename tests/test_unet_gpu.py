@@ -206,6 +206,44 @@ def test_train_step_vs_oracle(graph, monkeypatch):
     assert rel(trainer.state.params.shadow_flat_noupdate().float(), trainer.state.params.flat) < 4e-3
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_ddpm_train_step_vs_oracle(graph, monkeypatch):
+    """BASELINE configs[0] (the reference's own CPU-runnable case): unconditional DDPM UNet,
+    LinearNoiseSchedule(1000), epsilon prediction - two training steps against the oracle."""
+    torch.manual_seed(0)
+    res, B = 16, 4
+    model = Unet(attention_configs=(None,) * 4, dtype=torch.bfloat16)
+    trainer = GeneralDiffusionTrainer(model, adamw(1e-3), LinearNoiseSchedule(1000),
+                                      DiffusionInputConfig("image", (res, res, 3), []), rngs=4,
+                                      model_output_transform=EpsilonPredictionTransform(), device=dev,
+                                      use_cuda_graph=graph)
+    P = cpu_params(trainer.state.params, True)
+    ema = {k: v.detach().clone() for k, v in P.items()}
+    freqs = model._fourier_freqs(dev).cpu()
+    img = torch.randint(0, 256, (B, res, res, 3), dtype=torch.uint8)
+    step_fn = trainer._define_train_step(B)
+    opt = {}
+    for it, t in enumerate((torch.tensor([3, 250, 640, 999]), torch.tensor([0, 17, 500, 998]))):
+        noise = torch.randn(B, res, res, 3)
+        monkeypatch.setattr(utils, "device_normal",
+                            lambda key, shape, device, dtype=torch.float32, _n=noise: _n.to(device))
+        monkeypatch.setattr(utils, "device_randint",
+                            lambda key, shape, lo, hi, device, _t=t: _t.to(device=device, dtype=torch.int32))
+        trainer.state, loss, trainer.rngstate = step_fn(trainer.state, trainer.rngstate, {"image": img.clone()}, 0)
+        want = train_ref.ddpm_train_step(P, opt, img, noise, t, freqs, lr=1e-3, wd=1e-4, ema=ema, step=it + 1)
+        assert abs(loss.item() - want.item()) / want.item() < 2e-2, (it, loss.item(), want.item())
+    p0 = Unet(attention_configs=(None,) * 4).init(utils.split(utils.PRNGKey(4))[1], device=torch.device("cpu"))
+    cos_n = cos_a = cos_b = 0.0
+    for k, v in trainer.state.params.named.items():
+        d_got = v.cpu() - p0.named[k]
+        d_ref = P[k].detach() - p0.named[k]
+        cos_n += (d_got * d_ref).sum().item()
+        cos_a += d_got.pow(2).sum().item()
+        cos_b += d_ref.pow(2).sum().item()
+    assert cos_n / (cos_a * cos_b) ** 0.5 > 0.9
+    assert torch.isfinite(trainer.state.params.flat).all()
+
+
 @pytest.mark.parametrize("res,B,levels", [(32, 2, (None, {"heads": 8}, {"heads": 8}, {"heads": 8})),
                                           (64, 1, (None, None, {"heads": 8}, {"heads": 8}))])
 def test_text_cross_attention_forward_backward_vs_oracle(res, B, levels):
