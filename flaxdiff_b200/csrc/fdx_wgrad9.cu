@@ -15,8 +15,15 @@
 //     five TMEM accumulators (320 columns);
 //   * X traffic drops from 9 to 3*(TH+2)/TH boxes per block: 107 FLOP per L2 byte.
 // Tiles = (ci block, co block, pixel split); split-K partial sums are combined with f32 atomics.
+//
+// TRANSPOSED = true computes the same tile as D^T: M = 64 output channels (A = the dY box, MN-major), and
+// N = 192 = the three ky views x 64 input channels of ONE kx box (B, MN-major; the views are TW*128 B
+// apart = the descriptor's leading-dimension offset): three 64 x 192 x 16 MMAs per K step instead of five
+// 128 x 64 x 16 ones.  An M = 64 accumulator fills lanes 0-15 of each TMEM sub-partition, so kx = 0 and
+// kx = 1 are interleaved into columns 0..191 (lane offsets 0 / 16) and kx = 2 uses columns 192..383.
 #include "fdx_common.cuh"
 #include "../../include/fdx.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -37,6 +44,7 @@ __device__ __forceinline__ int tap_of_slot(int slot) {   // slot 0..8 -> tap ind
   return ky * 3 + kx;
 }
 
+template <bool TRANSPOSED>
 __global__ void __launch_bounds__(kThreads, 1)
 fdx_wgrad9_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                   const W9Dev p) {
@@ -95,7 +103,7 @@ fdx_wgrad9_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t idesc = TRANSPOSED ? umma_idesc_bf16(64, 192, 1, 1) : umma_idesc_bf16(128, 64, 1, 1);
       int stage = 0; uint32_t phase = 0, tphase = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const int sp = tile / (p.cib * p.cob);
@@ -107,6 +115,19 @@ fdx_wgrad9_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
           tc_fence_after();
           const uint32_t sx = smem_u32(smem + stage * stage_bytes);
           const uint32_t sy = sx + 3 * xbuf_bytes;
+          if constexpr (TRANSPOSED) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = umma_desc_sw128(sy + k * 2048, 8192, 1024);            // dY: 64 co x 16 px
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                // B = (ky, ci) columns of box kx: three 64-channel blocks, p.TW * 128 B apart
+                const uint64_t db = umma_desc_sw128(sx + kx * xbuf_bytes + k * 2048, p.TW * 128, 1024);
+                const uint32_t d = tmem_base + (kx == 2 ? 192u : 0u) + (kx == 1 ? (16u << 16) : 0u);
+                umma_f16(d, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+              }
+            }
+          } else
 #pragma unroll
           for (int g = 0; g < 5; ++g) {
             // slots 2g, 2g+1 (slot 9 does not exist: its rows are computed on slot 8's view and dropped)
@@ -139,6 +160,27 @@ fdx_wgrad9_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
       const int ci = cb * 64 + (row & 63);
       mbar_wait(tfull, tphase);
       tc_fence_after();
+      if constexpr (TRANSPOSED) {
+        // lane = output channel: rows 16 q + (lane & 15); lanes 0-15 hold kx = 0 (columns 0..191) and
+        // kx = 2 (columns 192..383), lanes 16-31 hold kx = 1 (columns 0..191); column = ky * 64 + ci
+        const int co = ob * 64 + q * 16 + (lane & 15);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 384; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+          tmem_ld_wait();
+          const int kx = c0 < 192 ? (lane >> 4) : 2;
+          const bool live = (c0 < 192 || lane < 16) && co < p.Cout;
+          if (live) {
+            const int cc = c0 < 192 ? c0 : c0 - 192;
+            const int ky = cc >> 6, ci0 = cb * 64 + (cc & 63);
+            float* out = p.dw + ((long long)(ky * 3 + kx) * p.Cin + ci0) * p.Cout + co;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ci0 + j < p.Cin) atomicAdd(out + (long long)j * p.Cout, __uint_as_float(v[j]));
+          }
+        }
+      } else
 #pragma unroll 1
       for (int g = 0; g < 5; ++g) {
         const int slot = 2 * g + (row >> 6);
@@ -226,12 +268,17 @@ int fdx_wgrad9_launch(const fdx_act* x, const fdx_act* dy, float* dw, cudaStream
   const int smem_bytes = kStages * stage_bytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    FDX_CUDA(cudaFuncSetAttribute(fdx_wgrad9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kStages * (3 * 6 * 16 * 128 + 64 * 128) + 1024 + 256));
+    const int max_smem = kStages * (3 * 6 * 16 * 128 + 64 * 128) + 1024 + 256;
+    FDX_CUDA(cudaFuncSetAttribute(fdx_wgrad9_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    FDX_CUDA(cudaFuncSetAttribute(fdx_wgrad9_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
   int grid = sms < d.ntiles ? sms : d.ntiles;
-  fdx_wgrad9_kernel<<<grid, kThreads, smem_bytes, stream>>>(mX, mY, d);
+  // transposed arrangement by default (22.5 vs 23.1 ms/step at C2); FDX_NO_WGRAD9T=1 selects the tap-pair one
+  if (!getenv("FDX_NO_WGRAD9T"))
+    fdx_wgrad9_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(mX, mY, d);
+  else
+    fdx_wgrad9_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(mX, mY, d);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }
