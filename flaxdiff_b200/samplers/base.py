@@ -173,10 +173,14 @@ class DiffusionSampler:
             return steps.astype(np.int16)[::-1].copy()
         if spacing == 'karras':
             rho = 7.0
-            sig = np.exp(np.linspace(np.log(f32(1.0)), np.log(f32(end_step / start_step)) if end_step > 0
-                                     else f32(-np.inf), diffusion_steps, dtype=f32)).astype(f32)
-            steps = np.clip((sig ** f32(1 / rho) - f32(self.min_inv_rho)) /
-                            f32(self.max_inv_rho - self.min_inv_rho), 0, 1) * f32(start_step)
+            # end_step = 0 makes sigma_min = 0 and log(0) = -inf: the reference's sequence degenerates to NaN ->
+            # int16 0 for every entry but the first product (samplers/common.py:213-228); reproduced as is
+            with np.errstate(invalid='ignore', divide='ignore'):
+                sig = np.exp(np.linspace(np.log(f32(1.0)), np.log(f32(end_step / start_step)) if end_step > 0
+                                         else f32(-np.inf), diffusion_steps, dtype=f32)).astype(f32)
+                steps = np.clip((sig ** f32(1 / rho) - f32(self.min_inv_rho)) /
+                                f32(self.max_inv_rho - self.min_inv_rho), 0, 1) * f32(start_step)
+                steps = np.where(np.isfinite(steps), steps, f32(0.0))
             return steps.astype(np.int16)
         if spacing == 'exponential':
             u = np.linspace(0, 1, diffusion_steps, dtype=f32)
