@@ -11,7 +11,7 @@ Names and layouts follow flax: conv kernels HWIO, dense kernels (in, out).
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import Dict, Iterable, List, Tuple
+from typing import Dict, Iterable, Tuple
 
 import torch
 

@@ -13,7 +13,7 @@ launch with per-sample coefficients computed from the schedule.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple, Union
+from typing import Dict, Tuple
 
 import numpy as np
 import torch
@@ -22,7 +22,7 @@ from .. import ops, utils
 from .._lib import FdxError
 from ..predictors import DiffusionPredictionTransform, _affine, _vec
 from ..schedulers import NoiseScheduler
-from ..utils import RandomMarkovState, clip_images
+from ..utils import RandomMarkovState
 
 
 def linspace_int16(start, stop, num: int) -> np.ndarray:

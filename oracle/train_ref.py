@@ -3,8 +3,6 @@ one sampler evaluation on the CPU in torch fp32, following trainer/general_diffu
 and samplers/common.py:96-109.  PARITY UNPINNED (see oracle/unet_ref.py)."""
 from __future__ import annotations
 
-import math
-import time
 
 import torch
 

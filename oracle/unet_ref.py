@@ -21,7 +21,7 @@ are the flax tree ({'a/b/kernel': tensor} flat names, HWIO conv kernels, (in,out
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Sequence
+from typing import Dict, Sequence
 
 import torch
 import torch.nn.functional as F
