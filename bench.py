@@ -389,7 +389,7 @@ def main():
         "launches_per_step": launches_per_step,
         "train_tflops": step_tflop / (ms_dev / 1e3),
         "train_frac_of_sustained_bf16": step_tflop / (ms_dev / 1e3) / tf_sust,
-        "roofline": {"bound": "tensor", "kernel": "fdx_tc_kernel (tcgen05 tap-GEMM; all conv/GEMM launches of one step)",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 engines fdx_tc / fdx_tct / fdx_wgrad9 (all conv and GEMM launches of one step)",
                      "achieved": tc_tflops, "peak": tf_sust, "unit": "TFLOP/s", "frac": tc_tflops / tf_sust,
                      "peak_source": f"{src} bf16_tflops_sustained", "launches": tc_calls, "ms_in_step": tc_ms,
                      "share_of_step": tc_ms / ms_dev, **roofline_traffic(args.workload, B)},
