@@ -78,3 +78,85 @@ def test_oracle_ddpm_train_step_configs0():
     assert any(not torch.equal(before[k], P[k].detach()) for k in P)          # AdamW moved the parameters
     l_lo = train_ref.ddpm_train_step(P, {}, img, noise, torch.tensor([0, 0]), freqs, lr=0.0, wd=0.0)
     assert l_lo < 1e-3 * l_hi
+
+
+# ---- closed-form known answers for the UNet primitives of oracle/unet_ref.py ---------------------------------
+def test_oracle_conv_same_padding_semantics():
+    """flax nn.Conv padding='SAME' as XLA computes it: stride 1 pads (1,1); stride 2 on an EVEN size pads (0,1)
+    (the extra pixel goes to the end), on an odd size (1,1).  Checked against explicit loops."""
+    import torch
+    from oracle import unet_ref as U
+    torch.manual_seed(0)
+    for h, stride in ((6, 1), (6, 2), (5, 2), (2, 2)):
+        x = torch.randn(1, h, h, 2)
+        w = torch.randn(3, 3, 2, 3)
+        b = torch.randn(3)
+        got = U.conv_same(x, w, b, stride=stride)
+        ho = -(-h // stride)
+        total = max((ho - 1) * stride + 3 - h, 0)
+        lo = total // 2
+        want = torch.zeros(1, ho, ho, 3)
+        for oy in range(ho):
+            for ox in range(ho):
+                acc = b.clone()
+                for ky in range(3):
+                    for kx in range(3):
+                        iy, ix = oy * stride + ky - lo, ox * stride + kx - lo
+                        if 0 <= iy < h and 0 <= ix < h:
+                            acc = acc + x[0, iy, ix] @ w[ky, kx]
+                want[0, oy, ox] = acc
+        assert got.shape == want.shape
+        assert torch.allclose(got, want, atol=1e-5), (h, stride)
+    assert (-(-6 // 2), max((3 - 1) * 2 + 3 - 6, 0) // 2) == (3, 0)       # even size, stride 2: nothing before, 1 after
+
+
+def test_oracle_groupnorm_rmsnorm_closed_form():
+    import torch
+    from oracle import unet_ref as U
+    # two groups of two channels over a 1x2 image: group 0 holds {1,2,3,4}, group 1 holds {10,10,10,10}
+    x = torch.tensor([[[[1., 2., 10., 10.], [3., 4., 10., 10.]]]])
+    y = U.group_norm(x, torch.ones(4), torch.zeros(4), 2, 0.0 + 1e-12)
+    m, v = 2.5, 1.25
+    want0 = (torch.tensor([1., 2., 3., 4.]) - m) / v ** 0.5
+    assert torch.allclose(y[0, 0, 0, :2], want0[:2], atol=1e-5) and torch.allclose(y[0, 0, 1, :2], want0[2:], atol=1e-5)
+    assert torch.all(y[..., 2:] == 0)                   # zero variance: fast variance max(0, E[x^2]-E[x]^2) = 0, x - mean = 0
+    # scale / bias are per channel and applied after normalisation; eps enters as rsqrt(var + eps)
+    y2 = U.group_norm(x, torch.tensor([2., 2., 1., 1.]), torch.tensor([0., 1., 5., 5.]), 2, 1.0)
+    assert torch.allclose(y2[0, 0, 0, 0], torch.tensor((1 - m) / (v + 1.0) ** 0.5 * 2)) and float(y2[0, 0, 0, 2]) == 5.0
+    r = U.rms_norm(torch.tensor([[3., 4.]]), torch.tensor([1., 2.]), 0.0)
+    assert torch.allclose(r, torch.tensor([[3 / 12.5 ** 0.5, 8 / 12.5 ** 0.5]]))
+
+
+def test_oracle_activations_and_time_embedding_known_values():
+    import math
+    import torch
+    from oracle import unet_ref as U
+    assert abs(float(U.swish(torch.tensor(1.0))) - 0.7310585786) < 1e-6          # 1 * sigmoid(1)
+    assert abs(float(U.gelu_tanh(torch.tensor(1.0))) - 0.8411919906) < 1e-6     # tanh approximation, not erf (0.8413447)
+    assert float(U.gelu_tanh(torch.tensor(0.0))) == 0.0
+    # FourierEmbedding: [sin(t * 2 pi f), cos(t * 2 pi f)] then Dense -> gelu -> Dense -> gelu; identity-like weights
+    f = torch.tensor([0.25, 0.5])
+    D = 4
+    P = {"TimeProjection_0/DenseGeneral_0/kernel": torch.eye(D), "TimeProjection_0/DenseGeneral_0/bias": torch.zeros(D),
+         "TimeProjection_0/DenseGeneral_1/kernel": torch.eye(D), "TimeProjection_0/DenseGeneral_1/bias": torch.zeros(D)}
+    e = U.time_embedding(torch.tensor([1.0]), f, P)
+    raw = torch.tensor([math.sin(math.pi / 2), math.sin(math.pi), math.cos(math.pi / 2), math.cos(math.pi)])
+    want = U.gelu_tanh(U.gelu_tanh(raw))
+    assert torch.allclose(e[0], want, atol=1e-6)
+
+
+def test_oracle_attention_is_scaled_dot_product_plus_input():
+    """TransformerBlock(only_pure_attention) = RMSNorm(x) + to_out(softmax(q k^T / sqrt(d)) v) (attention.py:170-174,
+    321-380); with identity projections, one head and scale 1 the result is computable by hand."""
+    import torch
+    from oracle import unet_ref as U
+    C = 4
+    x = torch.randn(1, 2, 2, C)
+    eye = torch.eye(C)
+    P = {"a/RMSNorm_0/scale": torch.ones(C),
+         "a/Attention/Attention2/to_q/kernel": eye.view(C, 1, C), "a/Attention/Attention2/to_k/kernel": eye.view(C, 1, C),
+         "a/Attention/Attention2/to_v/kernel": eye.view(C, 1, C), "a/Attention/Attention2/to_out_0/kernel": eye.view(1, C, C)}
+    got = U.attention_block(P, "a", x, heads=1)
+    xn = U.rms_norm(x, torch.ones(C), 1e-4).view(4, C)
+    att = torch.softmax(xn @ xn.T / C ** 0.5, dim=-1) @ xn
+    assert torch.allclose(got.view(4, C), xn + att, atol=1e-5)
