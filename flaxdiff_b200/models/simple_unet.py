@@ -138,6 +138,13 @@ class Unet:
         self.context_dim = context_dim
         if norm_groups <= 0:
             raise FdxError("Unet: norm_groups=0 (RMSNorm blocks) is not on the supported hot path")
+        # the kernels implement exactly one activation and one compute type: anything else must fail loudly
+        act_name = activation if isinstance(activation, str) else getattr(activation, "__name__", repr(activation))
+        if act_name not in ("swish", "silu"):
+            raise FdxError(f"Unet: activation {act_name!r} is not supported (the fused kernels implement swish / silu)")
+        if dtype is not None and dtype != torch.bfloat16:
+            raise FdxError(f"Unet: dtype={dtype} is not supported: the engine computes in bf16 with f32 accumulation "
+                           "(pass dtype=None or torch.bfloat16)")
         if output_channels != 3:
             raise FdxError("Unet: output_channels must be 3 (pixel-space configs of BASELINE.json)")
         if len(self.attention_configs) != len(self.feature_depths):
