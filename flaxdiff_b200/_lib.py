@@ -50,7 +50,22 @@ class fdx_gemm_desc(ctypes.Structure):
     ]
 
 
+class fdx_opt_desc(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int),
+        ("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
+        ("ema", ctypes.c_void_p), ("shadow_bf16", ctypes.c_void_p), ("n", ctypes.c_longlong),
+        ("lr", ctypes.c_float), ("b1", ctypes.c_float), ("b2", ctypes.c_float), ("eps", ctypes.c_float),
+        ("weight_decay", ctypes.c_float), ("step", ctypes.c_int), ("ema_decay", ctypes.c_float),
+        ("grad_scale", ctypes.c_float), ("gstats", ctypes.c_void_p), ("clip_norm", ctypes.c_float),
+        ("dyn_lr_bc", ctypes.c_void_p), ("dynscale", ctypes.c_void_p),
+        ("seg_offsets", ctypes.c_void_p), ("nseg", ctypes.c_int), ("seg_norms", ctypes.c_void_p),
+        ("u_ws", ctypes.c_void_p),
+    ]
+
+
 GEMM_KK, GEMM_KMN, GEMM_MNMN = 0, 1, 2
+OPT_ADAM, OPT_LAMB = 0, 1
 
 _lib: Optional[ctypes.CDLL] = None
 

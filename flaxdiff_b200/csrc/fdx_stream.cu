@@ -158,77 +158,7 @@ __global__ void affine_kernel(const AffineArgs p, int B, long long E) {
   }
 }
 
-// ---------------------------------------------------------------------------
-// fused AdamW + EMA + bf16 shadow refresh over a flat parameter buffer
-// ---------------------------------------------------------------------------
-__global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                 float* __restrict__ m, float* __restrict__ v,
-                                 float* __restrict__ ema, __nv_bfloat16* __restrict__ shadow,
-                                 long long n, float lr, float b1, float b2, float eps, float wd,
-                                 float bc1, float bc2, float ema_decay, float gscale,
-                                 const float* __restrict__ gnorm_sq, float clip_norm,
-                                 const float* __restrict__ dyn) {
-  // dyn (device) = {lr, 1-b1^t, 1-b2^t}: lets a CUDA graph replay the step with fresh values
-  if (dyn) { lr = dyn[0]; bc1 = dyn[1]; bc2 = dyn[2]; }
-  float gs = gscale;
-  if (gnorm_sq && clip_norm > 0.f) {
-    // optax.clip_by_global_norm: g * min(1, clip / ||g||)
-    const float nrm = sqrtf(*gnorm_sq) * gscale;
-    if (nrm > clip_norm) gs *= clip_norm / nrm;
-  }
-  const long long n4 = n / 4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-       i += (long long)gridDim.x * blockDim.x) {
-    float4 P = reinterpret_cast<float4*>(p)[i];
-    const float4 G = reinterpret_cast<const float4*>(g)[i];
-    float4 M = reinterpret_cast<float4*>(m)[i];
-    float4 V = reinterpret_cast<float4*>(v)[i];
-    float4 Em = reinterpret_cast<float4*>(ema)[i];
-    float pp[4] = {P.x, P.y, P.z, P.w}, gg[4] = {G.x, G.y, G.z, G.w};
-    float mm[4] = {M.x, M.y, M.z, M.w}, vv[4] = {V.x, V.y, V.z, V.w};
-    float ee[4] = {Em.x, Em.y, Em.z, Em.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float gj = gg[j] * gs;
-      mm[j] = b1 * mm[j] + (1.f - b1) * gj;
-      vv[j] = b2 * vv[j] + (1.f - b2) * gj * gj;
-      const float mh = mm[j] / bc1, vh = vv[j] / bc2;
-      pp[j] -= lr * (mh / (sqrtf(vh) + eps) + wd * pp[j]);
-      ee[j] = ema_decay * ee[j] + (1.f - ema_decay) * pp[j];
-    }
-    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
-    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-    reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-    reinterpret_cast<float4*>(ema)[i] = make_float4(ee[0], ee[1], ee[2], ee[3]);
-    if (shadow) {
-      uint2 o;
-      o.x = pack_bf16x2(pp[0], pp[1]);
-      o.y = pack_bf16x2(pp[2], pp[3]);
-      reinterpret_cast<uint2*>(shadow)[i] = o;
-    }
-  }
-}
-
-__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
-  float acc = 0.f;
-  const long long n4 = n / 4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(g)[i];
-    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-  }
-  acc = warp_sum(acc);
-  __shared__ float sh[32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) sh[wid] = acc;
-  __syncthreads();
-  if (wid == 0) {
-    float v = lane < (blockDim.x >> 5) ? sh[lane] : 0.f;
-    v = warp_sum(v);
-    if (lane == 0) atomicAdd(out, v);
-  }
-}
-
+// (the optimiser kernels live in fdx_optim.cu)
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                  long long n) {
   const long long n4 = n / 4;
@@ -434,30 +364,6 @@ int fdx_affine_combine(int n_in, const float* const* inputs, const float* coef1,
   a.clip = clip; a.clip_lo = clip_lo; a.clip_hi = clip_hi;
   const long long t4 = (long long)B * E / 4;
   affine_kernel<<<stream_grid(t4, 256), 256, 0, (cudaStream_t)stream>>>(a, B, E);
-  FDX_LAUNCH_CHECK();
-  return FDX_OK;
-}
-
-int fdx_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16,
-                       long long n, float lr, float b1, float b2, float eps, float weight_decay,
-                       int step, float ema_decay, float grad_scale, const float* gnorm_sq,
-                       float clip_norm, const float* dyn_lr_bc, void* stream) {
-  FDX_REQUIRE(p && g && m && v && ema, "adamw_ema: null pointer");
-  FDX_REQUIRE(n > 0 && n % 4 == 0, "adamw_ema: n=%lld must be a multiple of 4 (pad the flat buffer)", n);
-  FDX_REQUIRE(step >= 1, "adamw_ema: step counts from 1");
-  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
-  adamw_ema_kernel<<<stream_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, ema, (__nv_bfloat16*)shadow_bf16, n, lr, b1, b2, eps, weight_decay, bc1, bc2,
-      ema_decay, grad_scale, gnorm_sq, clip_norm, dyn_lr_bc);
-  FDX_LAUNCH_CHECK();
-  return FDX_OK;
-}
-
-int fdx_sumsq(const float* g, long long n, float* out, void* stream) {
-  FDX_REQUIRE(g && out && n > 0 && n % 4 == 0, "sumsq: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  FDX_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
-  sumsq_kernel<<<stream_grid(n / 4, 256), 256, 0, st>>>(g, n, out);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

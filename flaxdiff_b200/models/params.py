@@ -80,6 +80,11 @@ class FlatParams(dict):
         super().__init__({'params': nest(self.named)})
         self._shadow = None
         self._shadow_version = -1
+        # Generation of `.flat`'s CONTENTS.  libfdx kernels write the buffer through raw pointers, which
+        # torch's `_version` counter never sees, so every writer outside torch (fdx_adamw_ema_step, checkpoint
+        # loads) calls `touch()`; `shadow()` re-casts when either counter moved.
+        self.gen = 0
+        self._shadow_gen = -1
 
     # bf16 shadow of the whole buffer (weights read by the tensor-core kernels)
     def shadow(self) -> "OrderedDict[str, torch.Tensor]":
@@ -87,10 +92,19 @@ class FlatParams(dict):
         if self._shadow is None:
             self._shadow_flat = torch.empty(self.layout.total, dtype=torch.bfloat16, device=self.flat.device)
             self._shadow = self.layout.views(self._shadow_flat)
-        if self._shadow_version != self.flat._version:
+        if self._shadow_version != self.flat._version or self._shadow_gen != self.gen:
             ops.cast_f32_bf16(self.flat, self._shadow_flat)
             self._shadow_version = self.flat._version
+            self._shadow_gen = self.gen
         return self._shadow
+
+    def touch(self):
+        """`.flat` was modified behind torch's back (a libfdx kernel or an external copy)."""
+        self.gen += 1
+
+    def shadow_is_fresh(self) -> bool:
+        return (self._shadow is not None and self._shadow_version == self.flat._version
+                and self._shadow_gen == self.gen)
 
     def shadow_flat(self) -> torch.Tensor:
         self.shadow()
@@ -104,8 +118,10 @@ class FlatParams(dict):
         return self._shadow_flat
 
     def mark_shadow_fresh(self):
-        """The fused optimiser kernel refreshed the shadow itself."""
+        """The fused optimiser kernel rewrote `.flat` AND refreshed the shadow itself."""
+        self.gen += 1
         self._shadow_version = self.flat._version
+        self._shadow_gen = self.gen
 
     def clone(self) -> "FlatParams":
         return FlatParams(self.layout, self.flat.clone())

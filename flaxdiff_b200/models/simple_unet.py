@@ -523,9 +523,14 @@ class Unet:
                 (wq, wk, wv, wo), Lk)
 
     # ------------------------------------------------------------------ backward program
-    def backward(self, fp: FlatParams, saved: dict, dF: torch.Tensor, grads: FlatParams):
-        """Accumulates d(loss)/d(params) into `grads` (f32, caller zeroes it) given dF = dL/dF."""
+    def backward(self, fp: FlatParams, saved: dict, dF: torch.Tensor, grads: FlatParams, on_ready=None):
+        """Accumulates d(loss)/d(params) into `grads` (f32, caller zeroes it) given dF = dL/dF.
+        `on_ready(lo, streams)`: called after each block's backward has been issued; every parameter
+        gradient at flat offset >= lo is final once the work already queued on `streams` has run (the layout
+        follows the forward order, the backward walks it from the end) - the data-parallel trainer launches
+        its gradient all-reduce buckets from this hook (trainer.GradExchange)."""
         W, W16, Gd = fp.named, fp.shadow(), grads.named
+        lows = self._block_offsets(fp.layout) if on_ready is not None else None
         G = self.norm_groups
         emb16 = saved["emb16"]
         B = saved["B"]
@@ -617,11 +622,25 @@ class Unet:
                 _, _, x_bf16, dst = rec
                 dy = grad_of(dst)
                 side.run(lambda: ops.conv_in_wgrad(x_bf16, dy, Gd[name + "/conv/kernel"], Gd[name + "/conv/bias"]))
+            if on_ready is not None:
+                on_ready(lows[name], [torch.cuda.current_stream(), side.stream])
         side.join()
         # timestep-embedding MLP
         tp = "TimeProjection_0/DenseGeneral_"
         ops.time_embed_bwd(demb, saved["temb_saved"], W[tp + "1/kernel"], Gd[tp + "0/kernel"], Gd[tp + "0/bias"],
                            Gd[tp + "1/kernel"], Gd[tp + "1/bias"])
+
+    def _block_offsets(self, layout: ParamLayout) -> Dict[str, int]:
+        """First flat offset of each block's parameters (block = first path component of the names)."""
+        key = id(layout)
+        cache = self.__dict__.setdefault("_lows", {})
+        if key not in cache:
+            lows: Dict[str, int] = {}
+            for pname, (off, _) in layout.table.items():
+                head = pname.split('/', 1)[0]
+                lows[head] = min(lows.get(head, off), off)
+            cache[key] = lows
+        return cache[key]
 
     def _res_bwd(self, rec, W, W16, Gd, G, emb16, demb, want, grad_of, side):
         _, name, xin, dst, st1, a1, hmid, st2, a2 = rec

@@ -316,10 +316,83 @@ def adamw_ema_step(p, g, m, v, ema, shadow, lr, b1, b2, eps, weight_decay, step,
           "adamw_ema_step")
 
 
-def sumsq(g: torch.Tensor) -> torch.Tensor:
-    out = torch.empty(1, dtype=torch.float32, device=g.device)
-    check(load().fdx_sumsq(ptr(g), ctypes.c_longlong(g.numel()), ptr(out), stream_ptr()), "sumsq")
+def optimizer_step(kind: int, p, g, m, v, ema, shadow, lr, b1, b2, eps, weight_decay, step, ema_decay=0.999,
+                   grad_scale: float = 1.0, gstats=None, clip_norm: float = 0.0, dyn=None, dynscale=None,
+                   seg_offsets=None, seg_norms=None, u_ws=None):
+    """fdx_optimizer_step: adam / adamw / lamb update (+ optional EMA, bf16 shadow refresh, global-norm clip,
+    DynamicScale unscale-and-skip) over the flat buffers.  `ema=None` = TrainState.apply_gradients alone."""
+    d = _lib.fdx_opt_desc()
+    d.kind = kind
+    d.p, d.g, d.m, d.v = ptr(p), ptr(g), ptr(m), ptr(v)
+    d.ema, d.shadow_bf16, d.n = ptr(ema), ptr(shadow), p.numel()
+    d.lr, d.b1, d.b2, d.eps, d.weight_decay = lr, b1, b2, eps, weight_decay
+    d.step, d.ema_decay, d.grad_scale = step, ema_decay, grad_scale
+    d.gstats, d.clip_norm, d.dyn_lr_bc, d.dynscale = ptr(gstats), clip_norm, ptr(dyn), ptr(dynscale)
+    if seg_offsets is not None:
+        assert seg_offsets.dtype == torch.int64
+        d.seg_offsets, d.nseg = ptr(seg_offsets), seg_offsets.numel()
+        d.seg_norms, d.u_ws = ptr(seg_norms), ptr(u_ws)
+    check(load().fdx_optimizer_step(ctypes.byref(d), stream_ptr()), "optimizer_step")
+
+
+def ema_update(ema: torch.Tensor, p: torch.Tensor, decay: float):
+    """ema = decay * ema + (1 - decay) * p over the flat buffers (TrainState.apply_ema)."""
+    check(load().fdx_ema_update(ptr(ema), ptr(p), ctypes.c_longlong(p.numel()), ctypes.c_float(decay),
+                                stream_ptr()), "ema_update")
+
+
+def grad_stats(g: torch.Tensor) -> torch.Tensor:
+    """-> f32[2] = (sum g^2, number of non-finite elements)."""
+    out = torch.empty(2, dtype=torch.float32, device=g.device)
+    check(load().fdx_grad_stats(ptr(g), ctypes.c_longlong(g.numel()), ptr(out), stream_ptr()), "grad_stats")
     return out
+
+
+def sumsq(g: torch.Tensor) -> torch.Tensor:
+    return grad_stats(g)
+
+
+def dynscale_update(state3: torch.Tensor, gstats: torch.Tensor, growth_factor=2.0, backoff_factor=0.5,
+                    growth_interval=2000, minimum_scale=1.1754943508222875e-38):
+    check(load().fdx_dynscale_update(ptr(state3), ptr(gstats), ctypes.c_float(growth_factor),
+                                     ctypes.c_float(backoff_factor), ctypes.c_int(growth_interval),
+                                     ctypes.c_float(minimum_scale), stream_ptr()), "dynscale_update")
+
+
+# --------------------------------------------------------------------------- data-parallel exchange
+class Comm:
+    """fdx_comm handle: NCCL communicator bound inside libfdx (one per process).  `unique_id()` on rank 0,
+    broadcast the 128 bytes by any side channel, then `Comm(rank, world, id)` on every rank."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        check(load().fdx_comm_unique_id(buf), "comm_unique_id")
+        return buf.raw
+
+    def __init__(self, rank: int, world: int, uid: bytes):
+        assert len(uid) == 128
+        self._h = ctypes.c_void_p()
+        check(load().fdx_comm_init(ctypes.byref(self._h), ctypes.c_int(rank), ctypes.c_int(world),
+                                   ctypes.create_string_buffer(uid, 128)), "comm_init")
+        self.rank, self.world = rank, world
+
+    def allreduce_avg_(self, buf: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """In-place mean over ranks of a contiguous f32 CUDA tensor (a bucket of the flat gradient buffer)."""
+        assert buf.dtype == torch.float32 and buf.is_contiguous()
+        st = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+        check(load().fdx_comm_allreduce_avg(self._h, ptr(buf), ctypes.c_longlong(buf.numel()), st),
+              "comm_allreduce_avg")
+        return buf
+
+    def destroy(self):
+        if self._h:
+            check(load().fdx_comm_destroy(self._h), "comm_destroy")
+            self._h = ctypes.c_void_p()
+
+
+def nccl_version() -> int:
+    return int(load().fdx_comm_nccl_version())
 
 
 def cast_f32_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:

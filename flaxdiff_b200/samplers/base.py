@@ -13,7 +13,8 @@ launch with per-sample coefficients computed from the schedule.
 """
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from collections import OrderedDict
+from typing import Tuple
 
 import numpy as np
 import torch
@@ -81,7 +82,9 @@ class DiffusionSampler:
         if hasattr(noise_schedule, 'min_inv_rho') and hasattr(noise_schedule, 'max_inv_rho'):
             self.min_inv_rho = noise_schedule.min_inv_rho
             self.max_inv_rho = noise_schedule.max_inv_rho
-        self._graphs: Dict[tuple, _GraphedEval] = {}
+        # bounded caches (LRU): captured denoise-evaluation graphs and flax-tree -> FlatParams conversions
+        self._graphs: "OrderedDict[tuple, _GraphedEval]" = OrderedDict()
+        self._trees: "OrderedDict[int, tuple]" = OrderedDict()
 
     # ------------------------------------------------------------------ one model evaluation
     def _eval(self, fp, x_t: torch.Tensor, t: torch.Tensor, *conditioning):
@@ -114,23 +117,50 @@ class DiffusionSampler:
         x0, eps = _affine([x_t, Fm], [p, q], [r, u])
         return x0, eps, Fm
 
+    MAX_GRAPHS = 4      # captured graphs kept per sampler (each owns a private memory pool)
+    MAX_TREES = 2       # flax-tree -> FlatParams conversions kept per sampler
+
+    def _flat_for(self, params, device):
+        """FlatParams for `params`.  A plain flax tree is packed ONCE and remembered by identity (the tree is
+        kept alive so its id cannot be recycled; flax trees are immutable by convention): calling
+        sample_model / generate_samples repeatedly with the same tree neither re-packs nor re-captures."""
+        from ..models.params import FlatParams
+        if isinstance(params, FlatParams):
+            return params
+        hit = self._trees.get(id(params))
+        if hit is not None and hit[0] is params:
+            self._trees.move_to_end(id(params))
+            return hit[1]
+        fp = self.model._as_flat(params, device)
+        self._trees[id(params)] = (params, fp)
+        while len(self._trees) > self.MAX_TREES:
+            self._trees.popitem(last=False)
+        return fp
+
     def sample_model(self, params, x_t, t, *conditioning_inputs):
-        fp = self.model._as_flat(params, x_t.device)
+        fp = self._flat_for(params, x_t.device)
         t = torch.as_tensor(t, device=x_t.device)
         if t.dim() == 0:
             t = t.expand(x_t.shape[0])
         t = t.contiguous()
         if not self.use_cuda_graph:
             return self._eval(fp, x_t, t, *conditioning_inputs)
-        key = (id(fp), fp.flat._version, tuple(x_t.shape), t.dtype,
-               tuple((tuple(c.shape), c.data_ptr()) for c in conditioning_inputs))
+        # The graph reads the parameters through fp's bf16 shadow / f32 buffers BY POINTER, so new parameter
+        # VALUES (training steps, EMA updates, checkpoint loads) need no re-capture: the shadow is re-cast
+        # here when fp's generation moved (FlatParams.gen - torch's version counter does not see libfdx
+        # writes).  Conditioning tensors are copied into static graph inputs, so fresh tensors of the same
+        # shape reuse the graph.
+        key = (id(fp), tuple(x_t.shape), t.dtype, tuple((tuple(c.shape), c.dtype) for c in conditioning_inputs))
         ge = self._graphs.get(key)
+        fp.shadow()
         if ge is None:
-            fp.shadow()     # refresh bf16 weights outside the capture
-            conds = conditioning_inputs
-            ge = _GraphedEval(lambda a, b: self._eval(fp, a, b, *conds), [x_t, t])
+            ge = _GraphedEval(lambda a, b, *conds: self._eval(fp, a, b, *conds), [x_t, t, *conditioning_inputs])
             self._graphs[key] = ge
-        return ge(x_t, t)
+            while len(self._graphs) > self.MAX_GRAPHS:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
+        return ge(x_t, t, *conditioning_inputs)
 
     def post_process(self, samples: torch.Tensor) -> torch.Tensor:
         ones = torch.ones((1, samples.shape[0]), dtype=torch.float32, device=samples.device)
@@ -210,6 +240,8 @@ class DiffusionSampler:
             samples = priors.to(device=device, dtype=torch.float32).contiguous()
         if model_conditioning_inputs is None:
             model_conditioning_inputs = []
+
+        params = self._flat_for(params, device)        # a flax tree is packed once per call, not per step
 
         def sample_model_fn(x_t, t, *additional_inputs):
             return self.sample_model(params, x_t, t, *additional_inputs)

@@ -52,17 +52,26 @@ class SimpleExpNoiseScheduler(KarrasVENoiseScheduler):
                          *args, **kwargs)
         n = timesteps if (isinstance(timesteps, int) and timesteps > 1) else 1000
         self._sig = torch.exp(torch.linspace(math.log(sigma_min), math.log(sigma_max), n))
+        self._sig_dev = {}
+
+    def _sig_on(self, device) -> torch.Tensor:
+        """The sigma table on `device`, copied once (never inside a CUDA-graph capture: the first call
+        happens in the warm-up evaluation that precedes every capture)."""
+        key = str(device)
+        if key not in self._sig_dev:
+            self._sig_dev[key] = self._sig.to(device)
+        return self._sig_dev[key]
 
     @property
     def sigmas(self):
-        return self._sig.to(self._dev())
+        return self._sig_on(self._dev())
 
     def get_sigmas(self, steps):
         steps = as_steps(steps, self._dev())
         n = self._sig.shape[0]
         idx = steps.to(torch.int16).to(torch.int64)
         idx = torch.where(idx < 0, idx + n, idx).clamp_(0, n - 1)
-        return self._sig.to(idx.device)[idx]
+        return self._sig_on(idx.device)[idx]
 
 
 class EDMNoiseScheduler(KarrasVENoiseScheduler):

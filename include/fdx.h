@@ -162,14 +162,63 @@ int fdx_loss_fwd_bwd(const float* F, const float* x_t, const float* target, cons
 int fdx_affine_combine(int n_in, const float* const* inputs, const float* coef1, const float* coef2,
                        const float* bf16_scale, int B, long long E, float* out1, float* out2,
                        void* out_bf16, int clip, float clip_lo, float clip_hi, void* stream);
-/* optax adamw (training.py:598-608) + TrainState.apply_ema (trainer/diffusion_trainer.py:31-37)
- * + bf16 shadow-weight refresh over one flat buffer; optional clip_by_global_norm. */
+/* ---- optimiser / EMA / loss scaling over ONE flat f32 buffer (fdx_optim.cu) -------------------- */
+/* optax.adam / adamw / lamb (+ optax.clip_by_global_norm) as flax TrainState.apply_gradients does them
+ * (training.py:263-267,594-608; trainer/general_diffusion_trainer.py:311,327), fused with
+ * TrainState.apply_ema (trainer/diffusion_trainer.py:31-37) and the refresh of the bf16 weight shadow the
+ * tensor-core kernels read.  `ema` NULL = apply_gradients only.  The gradient the update sees is
+ *   g * grad_scale [/ dynscale[0]] * min(1, clip_norm / ||.||)          (||.|| from gstats[0])
+ * and with `dynscale` set the parameter / moment update is SKIPPED when gstats[1] > 0 (non-finite gradients,
+ * general_diffusion_trainer.py:313-318) while the EMA still runs on the unchanged parameters.
+ * lamb: seg_offsets = the nseg tensor start offsets (elements, ascending, first = 0, multiples of 4),
+ * seg_norms = f32 [nseg][2] scratch, u_ws = f32 [n] scratch (optax.scale_by_trust_ratio is per tensor). */
+#define FDX_OPT_ADAM 0 /* adam (weight_decay = 0) and adamw */
+#define FDX_OPT_LAMB 1
+typedef struct fdx_opt_desc {
+  int kind;
+  float* p; const float* g; float* m; float* v;
+  float* ema;               /* or NULL */
+  void* shadow_bf16;        /* or NULL */
+  long long n;              /* multiple of 4 */
+  float lr, b1, b2, eps, weight_decay;
+  int step;                 /* optimiser count after this step (>= 1): bias corrections */
+  float ema_decay;
+  float grad_scale;         /* e.g. 1/world after a sum all-reduce; 1 otherwise */
+  const float* gstats;      /* device f32[2] from fdx_grad_stats, or NULL */
+  float clip_norm;          /* 0 = no clipping */
+  const float* dyn_lr_bc;   /* device {lr, 1-b1^t, 1-b2^t} overriding lr/step (CUDA-graph replay), or NULL */
+  const float* dynscale;    /* device DynamicScale state {scale, fin_steps, last_finite}, or NULL */
+  const long long* seg_offsets; int nseg; float* seg_norms; float* u_ws;   /* lamb only */
+} fdx_opt_desc;
+int fdx_optimizer_step(const fdx_opt_desc* d, void* stream);
+/* adamw + EMA + shadow, the common case, without the descriptor (gnorm_sq = fdx_grad_stats output). */
 int fdx_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, void* shadow_bf16,
                        long long n, float lr, float b1, float b2, float eps, float weight_decay,
                        int step, float ema_decay, float grad_scale, const float* gnorm_sq,
                        float clip_norm, const float* dyn_lr_bc /* device {lr,1-b1^t,1-b2^t} or NULL */,
                        void* stream);
-int fdx_sumsq(const float* g, long long n, float* out, void* stream);
+/* TrainState.apply_ema on its own: ema = decay*ema + (1-decay)*p (trainer/diffusion_trainer.py:31-37). */
+int fdx_ema_update(float* ema, const float* p, long long n, float decay, void* stream);
+/* out2[0] = sum g^2 (optax.clip_by_global_norm), out2[1] = number of non-finite elements (DynamicScale's
+ * is_finite, flax/training/dynamic_scale.py via general_diffusion_trainer.py:308).  fdx_sumsq = same call. */
+int fdx_grad_stats(const float* g, long long n, float* out2, void* stream);
+int fdx_sumsq(const float* g, long long n, float* out2, void* stream);
+/* DynamicScale state update after a step: state3 = {scale, fin_steps, last_finite}; finite: after
+ * growth_interval finite steps scale *= growth_factor; non-finite: scale = max(scale*backoff, minimum). */
+int fdx_dynscale_update(float* state3, const float* gstats, float growth_factor, float backoff_factor,
+                        int growth_interval, float minimum_scale, void* stream);
+
+/* ---- data-parallel exchange (fdx_comm.cu): jax.lax.pmean of the gradients and the loss ---------------
+ * (trainer/general_diffusion_trainer.py:325,334,340-345).  NCCL is bound at run time (dlopen); one
+ * communicator per process, one process per GPU.  fdx_comm_allreduce_avg is asynchronous on `stream` and
+ * may be called on sub-ranges ("buckets") of the flat gradient buffer while the backward pass still runs. */
+typedef struct fdx_comm fdx_comm;
+int fdx_comm_unique_id(void* id128 /* 128 bytes out; rank 0 creates it, every rank passes it to init */);
+int fdx_comm_init(fdx_comm** out, int rank, int world, const void* id128);
+int fdx_comm_allreduce_avg(fdx_comm* c, float* buf, long long n, void* stream);   /* in place, mean over ranks */
+int fdx_comm_world(const fdx_comm* c, int* rank, int* world);
+int fdx_comm_nccl_version(void);      /* 0 when NCCL cannot be bound */
+int fdx_comm_destroy(fdx_comm* c);
 int fdx_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
 /* jax.image.resize(nearest) x2 (models/common.py:214-215) and its adjoint. */
 int fdx_upsample2x(const fdx_act* x, const fdx_act* y, void* stream);

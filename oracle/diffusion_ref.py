@@ -178,3 +178,100 @@ def adamw_ema(p, g, m, v, ema, step, lr, b1=0.9, b2=0.999, eps=1e-8, wd=0.0, dec
     p = p - lr * (mh / (np.sqrt(vh) + eps) + wd * p)
     ema = decay * ema + (1 - decay) * p
     return p, m, v, ema
+
+
+# ---- remaining sampler rules ------------------------------------------------------------------------
+def simplified_euler_step(x, x0, cs, ns):
+    """SimplifiedEulerSampler.take_next_step (samplers/euler.py:20-33)."""
+    cs, ns = _r(cs), _r(ns)
+    dt = ns - cs
+    dx = (x - x0) / cs
+    return x + dx * dt
+
+
+def simple_ddpm_step(x0, eps, noise, ca, cs, na, ns):
+    """SimpleDDPMSampler.take_next_step (samplers/ddpm.py:20-37)."""
+    ca, cs, na, ns = map(_r, (ca, cs, na, ns))
+    coeff = ((ns ** 2) * ca) / (cs * na)
+    gamma = np.sqrt(((ns ** 2) / (cs ** 2)) * (1 - (ca ** 2) / (na ** 2)))
+    return na * x0 + coeff * eps + noise * gamma
+
+
+def rk4_step(x, eps_fn, cs, ns):
+    """RK4Sampler.sample_step (samplers/rk4_sampler.py:19-33); eps_fn(x, sigma) = predicted noise of the
+    model evaluated at the timestep whose sigma is `sigma` (get_derivative :12-15)."""
+    cs, ns = _r(cs), _r(ns)
+    dt = ns - cs
+    k1 = eps_fn(x, cs)
+    k2 = eps_fn(x + 0.5 * k1 * dt, cs + 0.5 * dt)
+    k3 = eps_fn(x + 0.5 * k2 * dt, cs + 0.5 * dt)
+    k4 = eps_fn(x + k3 * dt, cs + dt)
+    return x + (((k1 + 2 * k2 + 2 * k3 + k4) * dt) / 6)
+
+
+def multistep_dpm_step(x, eps, cs, ns, history):
+    """MultiStepDPM.take_next_step (samplers/multistep_dpm.py:11-58); `history` = list of
+    {'eps', 'sigma'} dicts, appended to in place like the reference's self.history."""
+    cs4, ns4 = _r(cs), _r(ns)
+    dt = ns4 - cs4
+
+    def second(cn, csg, ln, lsg):
+        return (cn - ln) / (csg - lsg)
+
+    if len(history) == 0:
+        out = x + eps * dt
+    elif len(history) == 1:
+        l = history[-1]
+        out = x + eps * dt + 0.5 * second(eps, cs4, l["eps"], l["sigma"]) * dt ** 2
+    else:
+        l, m = history[-1], history[-2]
+        dx2 = second(eps, cs4, l["eps"], l["sigma"])
+        dx2l = second(l["eps"], l["sigma"], m["eps"], m["sigma"])
+        dx3 = (dx2 - dx2l) / (0.5 * ((cs4 + l["sigma"]) - (l["sigma"] + m["sigma"])))
+        out = x + eps * dt + 0.5 * dx2 * dt ** 2 + (1 / 6) * dx3 * dt ** 3
+    history.append({"eps": eps, "sigma": cs4})
+    return out
+
+
+def karras_timestep_of_sigma(sigma, T=1.0, sigma_min=0.002, sigma_max=80.0, rho=7.0):
+    """KarrasVENoiseScheduler.get_timesteps (schedulers/karras.py:34-45): inverse of karras_sigma."""
+    sigma = np.asarray(sigma, dtype=f32)
+    lo, hi = f32(sigma_min ** (1 / rho)), f32(sigma_max ** (1 / rho))
+    ramp = np.clip(((sigma + f32(1e-12)) ** f32(1 / rho) - hi) / (lo - hi), 0, 1)
+    return (np.clip(1 - ramp, 0, 1) * f32(T)).astype(f32)
+
+
+# ---- optimiser variants ---------------------------------------------------------------------------
+def clip_by_global_norm(grads, max_norm):
+    """optax.clip_by_global_norm (training.py:604-608): g * min(1, max_norm / ||g||_2) over ALL leaves."""
+    nrm = np.sqrt(sum(float(np.sum(np.square(g.astype(np.float64)))) for g in grads))
+    scale = 1.0 if nrm < max_norm else max_norm / nrm
+    return [(g * f32(scale)).astype(f32) for g in grads], nrm
+
+
+def lamb_step(ps, gs, ms, vs, step, lr, b1=0.9, b2=0.999, eps=1e-6, wd=0.0):
+    """optax.lamb (training.py:266): scale_by_adam -> add_decayed_weights(wd) -> scale_by_trust_ratio
+    (per leaf: ||p|| / ||u||, 1 where either norm is 0) -> scale(-lr).  Lists of leaves in, lists out."""
+    out_p, out_m, out_v = [], [], []
+    for p, g, m, v in zip(ps, gs, ms, vs):
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * g * g
+        u = (m / (1 - b1 ** step)) / (np.sqrt(v / (1 - b2 ** step)) + eps) + wd * p
+        pn, un = np.sqrt(np.sum(p.astype(np.float64) ** 2)), np.sqrt(np.sum(u.astype(np.float64) ** 2))
+        ratio = 1.0 if (pn == 0 or un == 0) else pn / un
+        out_p.append((p - lr * ratio * u).astype(f32))
+        out_m.append(m.astype(f32))
+        out_v.append(v.astype(f32))
+    return out_p, out_m, out_v
+
+
+def dynamic_scale_update(scale, fin_steps, is_finite, growth_factor=2.0, backoff_factor=0.5,
+                         growth_interval=2000, minimum_scale=float(np.finfo(np.float32).tiny)):
+    """flax.training.dynamic_scale.DynamicScale.value_and_grad's state update (used at
+    trainer/general_diffusion_trainer.py:305-318)."""
+    grow = fin_steps == growth_interval
+    fin_scale = min(scale * growth_factor, float(np.finfo(np.float32).max)) if (grow and is_finite) else scale
+    inf_scale = max(scale * backoff_factor, minimum_scale)
+    new_scale = fin_scale if is_finite else inf_scale
+    new_steps = 0 if (grow or not is_finite) else fin_steps + 1
+    return new_scale, new_steps
