@@ -64,6 +64,23 @@ class fdx_opt_desc(ctypes.Structure):
     ]
 
 
+class fdx_attn_desc(ctypes.Structure):
+    _fields_ = [
+        ("B", ctypes.c_int), ("heads", ctypes.c_int), ("L", ctypes.c_int), ("Lk", ctypes.c_int), ("dh", ctypes.c_int),
+        ("scale", ctypes.c_float),
+        ("q", ctypes.c_void_p), ("q_ld", ctypes.c_longlong), ("q_bs", ctypes.c_longlong),
+        ("k", ctypes.c_void_p), ("k_ld", ctypes.c_longlong), ("k_bs", ctypes.c_longlong),
+        ("v", ctypes.c_void_p), ("v_ld", ctypes.c_longlong), ("v_bs", ctypes.c_longlong),
+        ("o", ctypes.c_void_p), ("o_ld", ctypes.c_longlong), ("o_bs", ctypes.c_longlong),
+        ("lse", ctypes.c_void_p),
+        ("d_o", ctypes.c_void_p), ("do_ld", ctypes.c_longlong), ("do_bs", ctypes.c_longlong),
+        ("dvec_ws", ctypes.c_void_p),
+        ("dq", ctypes.c_void_p), ("dq_ld", ctypes.c_longlong), ("dq_bs", ctypes.c_longlong),
+        ("dk", ctypes.c_void_p), ("dk_ld", ctypes.c_longlong), ("dk_bs", ctypes.c_longlong),
+        ("dv", ctypes.c_void_p), ("dv_ld", ctypes.c_longlong), ("dv_bs", ctypes.c_longlong),
+    ]
+
+
 GEMM_KK, GEMM_KMN, GEMM_MNMN = 0, 1, 2
 OPT_ADAM, OPT_LAMB = 0, 1
 

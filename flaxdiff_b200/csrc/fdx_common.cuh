@@ -37,6 +37,8 @@ int fdx_check_cuda(cudaError_t e, const char* what);
   } while (0)
 
 void fdx_count_launch();
+// which tensor-core kernel family the most recent launch belonged to (bench.py attributes event times)
+void fdx_note_kernel(int kind);
 #define FDX_LAUNCH_CHECK()                 \
   do {                                     \
     fdx_count_launch();                    \

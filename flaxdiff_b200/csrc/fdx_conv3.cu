@@ -206,6 +206,7 @@ int launch_c3(const CUtensorMap& mA, const CUtensorMap& mB, const C3Dev& d, cuda
   int grid = fdx_num_sms();
   if (d.ntiles < grid) grid = d.ntiles;
   fdx_conv3_kernel<BN, B_MN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA, mB, d);
+  fdx_note_kernel(FDX_KERNEL_CONV3);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

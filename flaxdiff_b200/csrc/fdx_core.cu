@@ -1,5 +1,6 @@
 // fdx_core.cu -- error plumbing, device query and TMA descriptor encoding.
 #include "fdx_common.cuh"
+#include "../../include/fdx.h"
 #include <stdarg.h>
 #include <string.h>
 #include <mutex>
@@ -14,9 +15,11 @@ EncodeTiledFn g_encode = nullptr;
 std::once_flag g_encode_once;
 int g_sms = -1;
 unsigned long long g_launches = 0;
+int g_last_kind = -1;
 }  // namespace
 
 void fdx_count_launch() { ++g_launches; }
+void fdx_note_kernel(int kind) { g_last_kind = kind; }
 
 void fdx_set_error(const char* fmt, ...) {
   va_list ap;
@@ -98,4 +101,17 @@ const char* fdx_last_error(void) { return g_err; }
 int fdx_version(void) { return 100; }
 int fdx_device_sm_count(void) { return fdx_num_sms(); }
 unsigned long long fdx_launch_count(void) { return g_launches; }
+int fdx_last_kernel_kind(void) { return g_last_kind; }
+const char* fdx_kernel_kind_name(int kind) {
+  switch (kind) {
+    case FDX_KERNEL_TC: return "fdx_tc_kernel";
+    case FDX_KERNEL_TCT: return "fdx_tct_kernel";
+    case FDX_KERNEL_WGRAD9K: return "fdx_wgrad9k_kernel";
+    case FDX_KERNEL_WGRAD9: return "fdx_wgrad9_kernel";
+    case FDX_KERNEL_CONV3: return "fdx_conv3_kernel";
+    case FDX_KERNEL_ATTN_FWD: return "fdx_attn_fwd_kernel";
+    case FDX_KERNEL_ATTN_BWD: return "fdx_attn_bwd_kernel";
+  }
+  return "other";
+}
 }

@@ -468,6 +468,7 @@ int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d, cud
   if (grid <= 0) return FDX_ERR_NO_DEVICE;
   if (d.ntiles < grid) grid = d.ntiles;
   fdx_tc_kernel<BN, MODE, EPI, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA, mB, d);
+  fdx_note_kernel(FDX_KERNEL_TC);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }
@@ -499,6 +500,7 @@ int launch_pair(const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d, cu
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   FDX_CUDA(cudaLaunchKernelEx(&cfg, fdx_tc_kernel<BN, MODE, EPI_PLAIN, true>, mA, mB, d));
+  fdx_note_kernel(FDX_KERNEL_TC);
   fdx_count_launch();
   return FDX_OK;
 }

@@ -276,6 +276,7 @@ int launch_tct(const CUtensorMap& mW, const CUtensorMap& mX, const TctDev& d, cu
   if (grid <= 0) return FDX_ERR_NO_DEVICE;
   if (d.ntiles < grid) grid = d.ntiles;
   fdx_tct_kernel<MT, A_MN><<<grid, kThreads, smem, stream>>>(mW, mX, d);
+  fdx_note_kernel(FDX_KERNEL_TCT);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

@@ -213,6 +213,155 @@ fdx_wgrad9_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Round-2 arrangement ("ky pairs in M, kx in N").  The kernels above are bounded by the MMA SHAPE, not by
+// data movement: tcgen05 floor = max(M,128) * N / 256 cycles per K=16 step, so the transposed variant's three
+// M=64 x N=192 MMAs cost 3 * 96 = 288 cycles for work worth 144 (50 %), and the tap-pair variant's five
+// M=128 x N=64 MMAs are operand-read bound ((4 KB + 2 KB) / 128 B per cycle = 48 > 32).  Here the SHIFTS ARE
+// SPLIT between the operands:  dW[ky][kx][ci][co] = sum_px X[y+ky-1, x'][ci] * dY[y, x'-kx+1][co]
+//   * A (M) = the ky views of ONE X box (TH+2 rows, no x halo): rows of TW pixels are TW*128 B apart
+//             (1024-aligned), so (ky=0, ky=1) x 64 ci is one M=128 operand (descriptor LBO = TW*128) and
+//             ky=2 an M=64 one;
+//   * B (N) = THREE dY boxes shifted by kx-1 pixels (TMA zero-fills outside the image), contiguous in shared
+//             memory: N = 3 kx x 64 co = 192 (descriptor LBO = 8192).
+// Two MMAs per K=16 step, 96 + 96 = 192 cycles for 144 cycles' worth of work (75 % floor instead of 50 %),
+// 36 KB of TMA per 64-pixel block instead of 44 KB, and every accumulator row is (ky, ci) with the columns
+// (kx, co) contiguous in HWIO, so the split-K reduction is 16-byte red.global.add.v4.f32.
+// TMEM: columns [0,192) = ky 0/1 (128 lanes), [192,384) = ky 2 (lanes 0-15 of each sub-partition).
+__global__ void __launch_bounds__(kThreads, 1)
+fdx_wgrad9k_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+                   const W9Dev p) {
+  constexpr int S = 5;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int row_bytes = p.TW * 128;                      // one pixel row of the box: TW pixels x 64 channels
+  const int xbuf_bytes = (p.TH + 2) * row_bytes;         // multiple of 1024
+  const int ybuf_bytes = 64 * 128;
+  const int stage_bytes = xbuf_bytes + 3 * ybuf_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* tfull = bars + 2 * S;
+  uint64_t* tempty = bars + 2 * S + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapY);
+    for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long kblocks = (long long)p.nxb * p.nyb * p.nimg;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int r = tile;
+        const int cb = r % p.cib; r /= p.cib;
+        const int ob = r % p.cob; r /= p.cob;
+        const int sp = r;
+        const int pb0 = (int)((kblocks * sp) / p.splits), pb1 = (int)((kblocks * (sp + 1)) / p.splits);
+        for (int pb = pb0; pb < pb1; ++pb) {
+          const int xb = pb % p.nxb, yb = (pb / p.nxb) % p.nyb, nb = pb / (p.nxb * p.nyb);
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sx = smem + stage * stage_bytes;
+          uint8_t* sy = sx + xbuf_bytes;
+          mbar_arrive_expect_tx(&full[stage], stage_bytes);
+          tma_load_4d(sx, &mapX, &full[stage], cb * 64, xb * p.TW, yb * p.TH - 1, nb);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)     // dY[y, x' - kx + 1]
+            tma_load_4d(sy + kx * ybuf_bytes, &mapY, &full[stage], ob * 64, xb * p.TW + 1 - kx, yb * p.TH, nb);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc01 = umma_idesc_bf16(128, 192, 1, 1);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(64, 192, 1, 1);
+      int stage = 0; uint32_t phase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int sp = tile / (p.cib * p.cob);
+        const int nk = (int)((kblocks * (sp + 1)) / p.splits) - (int)((kblocks * sp) / p.splits);
+        mbar_wait(tempty, tphase ^ 1);
+        tc_fence_after();
+        for (int i = 0; i < nk; ++i) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sx = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sy = sx + xbuf_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t db = umma_desc_sw128(sy + k * 2048, 8192, 1024);              // 3 kx x 64 co
+            const uint64_t da01 = umma_desc_sw128(sx + k * 2048, row_bytes, 1024);       // ky 0 | ky 1
+            const uint64_t da2 = umma_desc_sw128(sx + 2 * row_bytes + k * 2048, 1024, 1024);
+            umma_f16(tmem_base, da01, db, idesc01, (i | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_base + 192u, da2, db, idesc2, (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull);
+        tphase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      int r = tile;
+      const int cb = r % p.cib; r /= p.cib;
+      const int ob = r % p.cob; r /= p.cob;
+      const int sp = r;
+      const bool has = ((int)((kblocks * (sp + 1)) / p.splits) - (int)((kblocks * sp) / p.splits)) > 0;
+      mbar_wait(tfull, tphase);
+      tc_fence_after();
+      // columns [0,192): row = 32 q + lane = (ky = row >> 6, ci = row & 63); columns [192,384): ky = 2,
+      // lanes 0-15 of this sub-partition = ci 16 q + lane
+#pragma unroll 1
+      for (int c0 = 0; c0 < 384; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const bool first = c0 < 192;
+        const int row = q * 32 + lane;
+        const int ky = first ? (row >> 6) : 2;
+        const int ci = cb * 64 + (first ? (row & 63) : (q * 16 + (lane & 15)));
+        const int cc = first ? c0 : c0 - 192;
+        const int kx = cc >> 6, co0 = ob * 64 + (cc & 63);
+        const bool live = has && (first || lane < 16) && ci < p.Cin && co0 < p.Cout;
+        if (live) {
+          float* out = p.dw + ((long long)(ky * 3 + kx) * p.Cin + ci) * p.Cout + co0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + j),
+                         "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                         "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      tphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 }  // namespace
 
 // Returns FDX_ERR_UNSUPPORTED (without setting an error) when the shape does not fit this kernel;
@@ -264,6 +413,24 @@ int fdx_wgrad9_launch(const fdx_act* x, const fdx_act* dy, float* dw, cudaStream
     int s = fdx_make_tmap_bf16(&mY, dy->ptr, 4, dims, str, box, est, 1);
     if (s != FDX_OK) return s;
   }
+  // default: the round-2 "ky pairs in M, kx in N" kernel; FDX_WGRAD9_V1=1 selects the round-1 kernels
+  // (transposed arrangement, or the tap-pair one with FDX_NO_WGRAD9T=1).  Cout must be a multiple of 32 for
+  // the 16-byte reductions (it is a multiple of 64 on every UNet layer).
+  if (!getenv("FDX_WGRAD9_V1")) {
+    const int stage_k = (d.TH + 2) * d.TW * 128 + 3 * 64 * 128;
+    const int smem_k = 5 * stage_k + 1024 + 256;
+    static bool attr_k = false;
+    if (!attr_k) {
+      FDX_CUDA(cudaFuncSetAttribute(fdx_wgrad9k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    5 * (6 * 16 * 128 + 3 * 64 * 128) + 1024 + 256));
+      attr_k = true;
+    }
+    const int gridk = sms < d.ntiles ? sms : d.ntiles;
+    fdx_wgrad9k_kernel<<<gridk, kThreads, smem_k, stream>>>(mX, mY, d);
+    fdx_note_kernel(FDX_KERNEL_WGRAD9K);
+    FDX_LAUNCH_CHECK();
+    return FDX_OK;
+  }
   const int stage_bytes = 3 * (d.TH + 2) * d.TW * 128 + 64 * 128;
   const int smem_bytes = kStages * stage_bytes + 1024 + 256;
   static bool attr_set = false;
@@ -279,6 +446,7 @@ int fdx_wgrad9_launch(const fdx_act* x, const fdx_act* dy, float* dw, cudaStream
     fdx_wgrad9_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(mX, mY, d);
   else
     fdx_wgrad9_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(mX, mY, d);
+  fdx_note_kernel(FDX_KERNEL_WGRAD9);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

@@ -480,6 +480,46 @@ class Unet:
 
     def _attn_fwd(self, name, xin: Node, dst: Node, heads, W, W16, ctx16=None):
         """TransformerBlock(only_pure_attention) (models/attention.py:321-380): xn = RMSNorm(x);
+        out = xn + to_out(softmax(q k^T / sqrt(d)) v), keys / values from `textcontext` (cross-attention,
+        77 x 768) or from xn itself.  q / k / v / out projections are tcgen05 GEMMs; the attention core is ONE
+        fused kernel (fdx_attention_fwd: logits and probabilities stay in TMEM / shared memory).  Heads
+        narrower than 32 are zero-padded to 32 (the kernel stores heads 32 or 64 wide).
+        FDX_ATTN_UNFUSED=1 selects the round-1 path (separate QK^T / softmax / PV launches)."""
+        if os.environ.get("FDX_ATTN_UNFUSED"):
+            return self._attn_fwd_unfused(name, xin, dst, heads, W, W16, ctx16)
+        x = xin.t
+        Bn, hh, ww, C = x.shape
+        L = hh * ww
+        d = C // heads
+        dp = 32 if d <= 32 else 64
+        if d > 64:
+            raise FdxError(f"attention: head width {d} > 64 is not supported")
+        HD = heads * dp
+        base = f"{name}/Attention/Attention2"
+        dev = x.device
+        xn = ops.rmsnorm_fwd(x, W[f"{name}/RMSNorm_0/scale"], ATTN_EPS)
+        x2 = xn.view(Bn * L, C)
+        if ctx16 is None:
+            ctx, Lk, Cc = xn.view(Bn, L, C), L, C
+        else:
+            ctx, Lk, Cc = ctx16, ctx16.shape[1], ctx16.shape[2]
+        wq = self._pad_heads(W16[f"{base}/to_q/kernel"], 2, d, dp).reshape(C, HD)
+        wk = self._pad_heads(W16[f"{base}/to_k/kernel"], 2, d, dp).reshape(Cc, HD)
+        wv = self._pad_heads(W16[f"{base}/to_v/kernel"], 2, d, dp).reshape(Cc, HD)
+        wo = self._pad_heads(W16[f"{base}/to_out_0/kernel"], 1, d, dp).reshape(HD, C)
+        q = ops.linear_fwd(x2, wq).view(Bn, L, HD)
+        k = torch.empty((Bn, Lk, HD), dtype=BF16, device=dev)
+        v = torch.empty((Bn, Lk, HD), dtype=BF16, device=dev)
+        ops.linear_fwd(ctx.reshape(Bn * Lk, Cc), wk, out=k.view(Bn * Lk, HD))
+        ops.linear_fwd(ctx.reshape(Bn * Lk, Cc), wv, out=v.view(Bn * Lk, HD))
+        o, lse = ops.attention_fwd(q, k, v, heads, dp, d ** -0.5)
+        out2 = dst.t
+        ops.gemm(GEMM_KMN, o, wo, out2, Bn * L, C, HD, HD, C, out2.stride(2), res=xn, r_ld=C)
+        return ("attn", name, xin, dst, heads, xn, q, k, v, lse, o, ctx if ctx16 is not None else None,
+                (wq, wk, wv, wo), Lk)
+
+    def _attn_fwd_unfused(self, name, xin: Node, dst: Node, heads, W, W16, ctx16=None):
+        """Round-1 attention path (FDX_ATTN_UNFUSED=1): xn = RMSNorm(x);
         out = xn + to_out(softmax(q k^T / sqrt(d)) v); keys/values come from `textcontext`
         (cross-attention, e.g. 77 x 768) or from xn itself (self-attention).  Heads narrower than 32
         and key counts that are not multiples of 32 are zero-padded for the tensor-core tiles."""
@@ -519,7 +559,7 @@ class Unet:
                  a_s=(L * Lkp, heads * L * Lkp), b_s=(dp, Lkp * HD), d_s=(dp, L * HD))
         out2 = dst.t
         ops.gemm(GEMM_KMN, o, wo, out2, Bn * L, C, HD, HD, C, out2.stride(2), res=xn, r_ld=C)
-        return ("attn", name, xin, dst, heads, xn, q, k, v, P, o, ctx if ctx16 is not None else None,
+        return ("attn_unfused", name, xin, dst, heads, xn, q, k, v, P, o, ctx if ctx16 is not None else None,
                 (wq, wk, wv, wo), Lk)
 
     # ------------------------------------------------------------------ backward program
@@ -593,6 +633,8 @@ class Unet:
                     mark_children_written(xin, children[id(xin)])
             elif kind == "attn":
                 self._attn_bwd(rec, W, W16, Gd, want, grad_of)
+            elif kind == "attn_unfused":
+                self._attn_bwd_unfused(rec, W, W16, Gd, want, grad_of)
             elif kind == "conv":
                 _, _, xin, dst = rec
                 dy = grad_of(dst)
@@ -696,6 +738,61 @@ class Unet:
             ops.act_add(dx, dout, dx)
 
     def _attn_bwd(self, rec, W, W16, Gd, want, grad_of):
+        """Backward of _attn_fwd: projection GEMMs around fdx_attention_bwd (dQ / dK / dV with the logits
+        recomputed on chip from the saved log-sum-exp)."""
+        _, name, xin, dst, heads, xn, q, k, v, lse, o, ctx, (wq, wk, wv, wo), Lk = rec
+        x = xin.t
+        Bn, hh, ww, C = x.shape
+        L = hh * ww
+        d = C // heads
+        dp = 32 if d <= 32 else 64
+        HD = heads * dp
+        cross = ctx is not None
+        kv_src = ctx if cross else xn.view(Bn, L, C)
+        Cc = kv_src.shape[2]
+        base = f"{name}/Attention/Attention2"
+        dout = grad_of(dst)
+        M = Bn * L
+        dev = x.device
+
+        def grad_target(pname, shape_p):
+            g = Gd[pname]
+            if dp == d:
+                return g.view(shape_p), None
+            return torch.zeros(shape_p, dtype=F32, device=dev), g
+
+        def finish(tmp, g, axis_view, sl):
+            if g is not None:
+                g.add_(tmp.view(axis_view)[sl])
+
+        o2 = o.view(M, HD)
+        t_o, g_o = grad_target(f"{base}/to_out_0/kernel", (HD, C))
+        ops.gemm(GEMM_MNMN, o2, dout, t_o, HD, C, M, HD, dout.stride(2), C, atomic=True, reduce_batch=True)
+        finish(t_o, g_o, (heads, dp, C), (slice(None), slice(0, d), slice(None)))
+        do = torch.empty((Bn, L, HD), dtype=BF16, device=dev)
+        ops.gemm(GEMM_KK, dout, wo, do, M, HD, C, dout.stride(2), C, HD)
+        dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, heads, dp, d ** -0.5)
+        dq2, dk2, dv2 = dq.view(M, HD), dk.view(Bn * Lk, HD), dv.view(Bn * Lk, HD)
+        x2 = xn.view(M, C)
+        t_q, g_q = grad_target(f"{base}/to_q/kernel", (C, HD))
+        ops.gemm(GEMM_MNMN, x2, dq2, t_q, C, HD, M, C, HD, HD, atomic=True, reduce_batch=True)
+        finish(t_q, g_q, (C, heads, dp), (slice(None), slice(None), slice(0, d)))
+        src2 = kv_src.reshape(Bn * Lk, Cc)
+        for nm, dy_ in (("to_k", dk2), ("to_v", dv2)):
+            t_w, g_w = grad_target(f"{base}/{nm}/kernel", (Cc, HD))
+            ops.gemm(GEMM_MNMN, src2, dy_, t_w, Cc, HD, Bn * Lk, Cc, HD, HD, atomic=True, reduce_batch=True)
+            finish(t_w, g_w, (Cc, heads, dp), (slice(None), slice(None), slice(0, d)))
+        # d(xn) = dout (residual) + dq Wq^T (+ dk Wk^T + dv Wv^T for self-attention)
+        dxn = torch.empty((Bn, hh, ww, C), dtype=BF16, device=dev)
+        dxn2 = dxn.view(M, C)
+        ops.gemm(GEMM_KK, dq2, wq, dxn2, M, C, HD, HD, HD, C, res=dout, r_ld=dout.stride(2))
+        if not cross:
+            for dy_, w_ in ((dk2, wk), (dv2, wv)):
+                ops.gemm(GEMM_KK, dy_, w_, dxn2, M, C, HD, HD, HD, C, res=dxn2, r_ld=C)
+        dx, acc = want(xin)
+        ops.rmsnorm_bwd(x, dxn, W[f"{name}/RMSNorm_0/scale"], ATTN_EPS, dx, Gd[f"{name}/RMSNorm_0/scale"], acc)
+
+    def _attn_bwd_unfused(self, rec, W, W16, Gd, want, grad_of):
         _, name, xin, dst, heads, xn, q, k, v, P, o, ctx, (wq, wk, wv, wo), Lk = rec
         x = xin.t
         Bn, hh, ww, C = x.shape

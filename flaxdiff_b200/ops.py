@@ -591,6 +591,52 @@ def conv_out_wgrad_direct(x, dF, dw, dbias):
                                     stream_ptr()), "conv_out_wgrad")
 
 
+# --------------------------------------------------------------------------- fused attention
+def _attn_desc(q, k, v, o, lse, heads: int, dh: int, scale: float):
+    """q / o: [B, L, heads*dh], k / v: [B, Lk, heads*dh] (bf16, last dim contiguous)."""
+    B, L, HD = q.shape
+    Lk = k.shape[1]
+    assert HD == heads * dh and k.shape[2] == HD and v.shape == k.shape and o.shape == q.shape
+    for t in (q, k, v, o):
+        assert t.dtype == torch.bfloat16 and t.stride(2) == 1
+    a = _lib.fdx_attn_desc()
+    a.B, a.heads, a.L, a.Lk, a.dh, a.scale = B, heads, L, Lk, dh, scale
+    a.q, a.q_ld, a.q_bs = ptr(q), q.stride(1), q.stride(0)
+    a.k, a.k_ld, a.k_bs = ptr(k), k.stride(1), k.stride(0)
+    a.v, a.v_ld, a.v_bs = ptr(v), v.stride(1), v.stride(0)
+    a.o, a.o_ld, a.o_bs = ptr(o), o.stride(1), o.stride(0)
+    a.lse = ptr(lse)
+    return a
+
+
+def attention_fwd(q, k, v, heads: int, dh: int, scale: float, out=None):
+    """o = softmax(q k^T * scale) v per (image, head) - fdx_attention_fwd.  -> (o bf16 [B, L, heads*dh],
+    lse f32 [B, heads, L]).  No (B, h, L, Lk) tensor exists in HBM."""
+    B, L, HD = q.shape
+    o = out if out is not None else torch.empty((B, L, HD), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B, heads, L), dtype=torch.float32, device=q.device)
+    a = _attn_desc(q, k, v, o, lse, heads, dh, scale)
+    check(load().fdx_attention_fwd(ctypes.byref(a), stream_ptr()), "attention_fwd")
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, lse, d_o, heads: int, dh: int, scale: float):
+    """-> (dq [B, L, HD], dk, dv [B, Lk, HD]) bf16 - fdx_attention_bwd (S / P recomputed on chip)."""
+    assert d_o.shape == q.shape and d_o.dtype == torch.bfloat16 and d_o.stride(2) == 1
+    dq = torch.empty_like(q, memory_format=torch.contiguous_format)
+    dk = torch.empty(tuple(k.shape), dtype=torch.bfloat16, device=k.device)
+    dv = torch.empty(tuple(v.shape), dtype=torch.bfloat16, device=v.device)
+    ws = torch.empty_like(lse)
+    a = _attn_desc(q, k, v, o, lse, heads, dh, scale)
+    a.d_o, a.do_ld, a.do_bs = ptr(d_o), d_o.stride(1), d_o.stride(0)
+    a.dvec_ws = ptr(ws)
+    a.dq, a.dq_ld, a.dq_bs = ptr(dq), dq.stride(1), dq.stride(0)
+    a.dk, a.dk_ld, a.dk_bs = ptr(dk), dk.stride(1), dk.stride(0)
+    a.dv, a.dv_ld, a.dv_bs = ptr(dv), dv.stride(1), dv.stride(0)
+    check(load().fdx_attention_bwd(ctypes.byref(a), stream_ptr()), "attention_bwd")
+    return dq, dk, dv
+
+
 # --------------------------------------------------------------------------- temb / softmax
 def time_embed_fwd(t, freqs, W1, b1, W2, b2):
     B, D = t.shape[0], W1.shape[0]

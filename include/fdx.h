@@ -39,6 +39,17 @@ int fdx_version(void);
 int fdx_device_sm_count(void);
 /* number of libfdx kernels launched (or captured into a CUDA graph) by this process so far */
 unsigned long long fdx_launch_count(void);
+/* tensor-core kernel family of the most recent launch (-1 = none yet) and its SASS-visible kernel name: lets a
+ * profiler attribute a CUDA-event interval around one C-ABI call to the kernel that ran (bench.py roofline). */
+#define FDX_KERNEL_TC 0       /* fdx_tc_kernel: pixels-as-M tap-GEMM engine */
+#define FDX_KERNEL_TCT 1      /* fdx_tct_kernel: transposed (weights-as-M) engine */
+#define FDX_KERNEL_WGRAD9K 2  /* fdx_wgrad9k_kernel: nine-tap weight gradient, ky pairs in M / kx in N */
+#define FDX_KERNEL_WGRAD9 3   /* fdx_wgrad9_kernel: round-1 nine-tap weight gradient */
+#define FDX_KERNEL_CONV3 4    /* fdx_conv3_kernel: halo-sharing forward (opt-in) */
+#define FDX_KERNEL_ATTN_FWD 5 /* fdx_attn_fwd_kernel: fused attention forward */
+#define FDX_KERNEL_ATTN_BWD 6 /* fdx_attn_bwd_kernel: fused attention backward */
+int fdx_last_kernel_kind(void);
+const char* fdx_kernel_kind_name(int kind);
 
 /* ---- tensor-core contractions (tcgen05 + TMA + TMEM) ------------------------- */
 /* flax nn.Conv 3x3 SAME, stride 1 or 2 (models/common.py:166-172, 237-244).
@@ -262,6 +273,33 @@ int fdx_time_embed_bwd(const float* demb, const float* four, const float* h1, co
 int fdx_softmax_fwd(const float* S, long long rows, int L, int Lp, void* P_bf16, void* stream);
 int fdx_softmax_bwd(const void* P_bf16, const float* dP, long long rows, int L, int Lp, float scale,
                     void* dS_bf16, void* stream);
+
+/* ---- fused attention (fdx_attn.cu) ------------------------------------------------------------------
+ * nn.dot_product_attention inside NormalAttention (models/attention.py:156-177): o = softmax(q k^T * scale) v
+ * per (image, head), self-attention (Lk = L) or cross-attention to the text context (Lk = 77), and its
+ * backward under jax.value_and_grad (trainer/general_diffusion_trainer.py:321).  The logits and probabilities
+ * never reach HBM: flash-style tcgen05 kernels with S / P in TMEM / shared memory; the backward recomputes
+ * them from `lse` (two kernels: dQ per query tile, dK + dV per key block; deterministic, no atomics).
+ * Tensors: bf16 [B][rows][heads*dh], `*_ld` = elements between rows, `*_bs` = elements between images;
+ * dh (as STORED) is 32 or 64 - narrower heads are zero-padded by the caller, `scale` = 1/sqrt(true width).
+ * lse: f32 [B][heads][L] (written by fwd, read by bwd); dvec_ws: f32 [B][heads][L] scratch (bwd). */
+typedef struct fdx_attn_desc {
+  int B, heads, L, Lk, dh;
+  float scale;
+  const void* q; long long q_ld, q_bs;
+  const void* k; long long k_ld, k_bs;
+  const void* v; long long v_ld, v_bs;
+  void* o; long long o_ld, o_bs;          /* fwd: output; bwd: the saved forward output (input) */
+  float* lse;
+  /* backward only */
+  const void* d_o; long long do_ld, do_bs;
+  float* dvec_ws;
+  void* dq; long long dq_ld, dq_bs;
+  void* dk; long long dk_ld, dk_bs;
+  void* dv; long long dv_ld, dv_bs;
+} fdx_attn_desc;
+int fdx_attention_fwd(const fdx_attn_desc* a, void* stream);
+int fdx_attention_bwd(const fdx_attn_desc* a, void* stream);
 
 #ifdef __cplusplus
 }
