@@ -150,10 +150,15 @@ class Unet:
         if len(self.attention_configs) != len(self.feature_depths):
             raise FdxError("Unet: attention_configs must have one entry per level")
         for c in self.attention_configs:
-            if c is not None and not c.get("only_pure_attention", True):
-                raise FdxError("Unet: only_pure_attention=False is not implemented yet")
-            if c is not None and c.get("use_projection", False):
-                raise FdxError("Unet: use_projection=True is not implemented yet")
+            if c is None:
+                continue
+            if c.get("flash_attention", False):
+                raise FdxError("Unet: flash_attention=True (EfficientAttention / jax pallas) has no counterpart here; "
+                               "the fused attention kernel is always used")
+            if not c.get("norm_inputs", True):
+                raise FdxError("Unet: norm_inputs=False is not supported")
+            if not c.get("only_pure_attention", True) and not c.get("explicitly_add_residual", True):
+                raise FdxError("Unet: explicitly_add_residual=False is not supported")
         self._n1 = "GroupNorm_0" if named_norms else "norm1"
         self._n2 = "GroupNorm_1" if named_norms else "norm2"
         self._nout = "GroupNorm_0" if named_norms else "conv_out_norm"
@@ -231,13 +236,35 @@ class Unet:
                 specs += [(f"{name}/ConvLayer_0/conv/kernel", (3, 3, cin, cout)),
                           (f"{name}/ConvLayer_0/conv/bias", (cout,))]
             elif kind == "attn":
-                h = cout["heads"]
+                # TransformerBlock (models/attention.py:305-380); names as flax generates them
+                acfg = cout
+                h = acfg["heads"]
                 d = cin // h
-                base = f"{name}/Attention/Attention2"
                 cctx = self.context_dim if self.context_dim else cin
-                specs += [(f"{name}/RMSNorm_0/scale", (cin,)),
-                          (f"{base}/to_q/kernel", (cin, h, d)), (f"{base}/to_k/kernel", (cctx, h, d)),
-                          (f"{base}/to_v/kernel", (cctx, h, d)), (f"{base}/to_out_0/kernel", (h, d, cin))]
+                pure = acfg.get("only_pure_attention", True)
+                proj = acfg.get("use_projection", False)
+                specs += [(f"{name}/RMSNorm_0/scale", (cin,))]
+                if proj:
+                    specs += [(f"{name}/project_in/kernel", (cin, cin))]
+
+                def mha(base, kdim):
+                    return [(f"{base}/to_q/kernel", (cin, h, d)), (f"{base}/to_k/kernel", (kdim, h, d)),
+                            (f"{base}/to_v/kernel", (kdim, h, d)), (f"{base}/to_out_0/kernel", (h, d, cin))]
+                if pure:
+                    specs += mha(f"{name}/Attention/Attention2", cctx)
+                else:
+                    if acfg.get("use_self_and_cross", True):
+                        specs += mha(f"{name}/Attention/Attention1", cin)
+                    specs += mha(f"{name}/Attention/Attention2", cctx)
+                    specs += [(f"{name}/Attention/ff/net_0/proj/kernel", (cin, 8 * cin)),
+                              (f"{name}/Attention/ff/net_0/proj/bias", (8 * cin,)),
+                              (f"{name}/Attention/ff/net_2/kernel", (4 * cin, cin)),
+                              (f"{name}/Attention/ff/net_2/bias", (cin,))]
+                    if acfg.get("use_self_and_cross", True):
+                        specs += [(f"{name}/Attention/norm1/scale", (cin,))]
+                    specs += [(f"{name}/Attention/norm2/scale", (cin,)), (f"{name}/Attention/norm3/scale", (cin,))]
+                if proj:
+                    specs += [(f"{name}/project_out/kernel", (cin, cin))]
         specs += [(f"{self._nout}/scale", (self.feature_depths[0],)), (f"{self._nout}/bias", (self.feature_depths[0],))]
         return specs
 
@@ -409,7 +436,10 @@ class Unet:
                 cur = dst
             elif kind == "attn":
                 dst = out_node(idx, h, w, cin)
-                rec = self._attn_fwd(name, cur, dst, cout["heads"], W, W16, ctx16)
+                if cout.get("only_pure_attention", True) and not cout.get("use_projection", False):
+                    rec = self._attn_fwd(name, cur, dst, cout["heads"], W, W16, ctx16)
+                else:
+                    rec = self._tblock_fwd(name, cur, dst, cout, W, W16, ctx16)
                 tape.append(rec)
                 cur = dst
             elif kind == "down":
@@ -562,6 +592,222 @@ class Unet:
         return ("attn_unfused", name, xin, dst, heads, xn, q, k, v, P, o, ctx if ctx16 is not None else None,
                 (wq, wk, wv, wo), Lk)
 
+
+    # ------------------------------------------------------------------ full transformer block (f3)
+    def _mha_fwd(self, base, xq: torch.Tensor, ctx: torch.Tensor, heads: int, W16, res: torch.Tensor,
+                 out: torch.Tensor):
+        """NormalAttention (models/attention.py:117-177) on 2-D token matrices: out = res + to_out(attn(
+        to_q(xq), to_k(ctx), to_v(ctx))).  xq [B, L, C], ctx [B, Lk, Cc] bf16; res / out [B*L, C]."""
+        Bn, L, C = xq.shape
+        Lk, Cc = ctx.shape[1], ctx.shape[2]
+        d = C // heads
+        dp = 32 if d <= 32 else 64
+        if d > 64:
+            raise FdxError(f"attention: head width {d} > 64 is not supported")
+        HD = heads * dp
+        wq = self._pad_heads(W16[f"{base}/to_q/kernel"], 2, d, dp).reshape(C, HD)
+        wk = self._pad_heads(W16[f"{base}/to_k/kernel"], 2, d, dp).reshape(Cc, HD)
+        wv = self._pad_heads(W16[f"{base}/to_v/kernel"], 2, d, dp).reshape(Cc, HD)
+        wo = self._pad_heads(W16[f"{base}/to_out_0/kernel"], 1, d, dp).reshape(HD, C)
+        q = ops.linear_fwd(xq.reshape(Bn * L, C), wq).view(Bn, L, HD)
+        k = ops.linear_fwd(ctx.reshape(Bn * Lk, Cc), wk).view(Bn, Lk, HD)
+        v = ops.linear_fwd(ctx.reshape(Bn * Lk, Cc), wv).view(Bn, Lk, HD)
+        o, lse = ops.attention_fwd(q, k, v, heads, dp, d ** -0.5)
+        ops.gemm(GEMM_KMN, o, wo, out, Bn * L, C, HD, HD, C, out.stride(0), res=res, r_ld=res.stride(0))
+        return (base, xq, ctx, heads, q, k, v, o, lse, (wq, wk, wv, wo))
+
+    def _mha_bwd(self, saved, dout: torch.Tensor, Gd):
+        """-> (d xq [B*L, C], d ctx [B*Lk, Cc]) bf16 given dout = d(out) [B*L, C] (the residual path is the
+        caller's); accumulates the four projection-kernel gradients."""
+        base, xq, ctx, heads, q, k, v, o, lse, (wq, wk, wv, wo) = saved
+        Bn, L, C = xq.shape
+        Lk, Cc = ctx.shape[1], ctx.shape[2]
+        d = C // heads
+        dp = 32 if d <= 32 else 64
+        HD = heads * dp
+        M, Mk = Bn * L, Bn * Lk
+        dev = xq.device
+
+        def wgrad(pname, src2, dy2, rows, kin, shape_view, sl):
+            g = Gd[pname]
+            if dp == d:
+                ops.gemm(GEMM_MNMN, src2, dy2, g.view(-1, dy2.shape[1]) if shape_view is None else g.view(shape_view),
+                         kin, dy2.shape[1], rows, src2.stride(0), dy2.stride(0), dy2.shape[1], atomic=True,
+                         reduce_batch=True)
+            else:
+                tmp = torch.zeros((kin, dy2.shape[1]), dtype=F32, device=dev)
+                ops.gemm(GEMM_MNMN, src2, dy2, tmp, kin, dy2.shape[1], rows, src2.stride(0), dy2.stride(0),
+                         dy2.shape[1], atomic=True, reduce_batch=True)
+                g.add_(tmp.view(sl[0])[sl[1]])
+
+        o2 = o.view(M, HD)
+        g_o = Gd[f"{base}/to_out_0/kernel"]
+        if dp == d:
+            ops.gemm(GEMM_MNMN, o2, dout, g_o.view(HD, C), HD, C, M, HD, dout.stride(0), C, atomic=True,
+                     reduce_batch=True)
+        else:
+            tmp = torch.zeros((HD, C), dtype=F32, device=dev)
+            ops.gemm(GEMM_MNMN, o2, dout, tmp, HD, C, M, HD, dout.stride(0), C, atomic=True, reduce_batch=True)
+            g_o.add_(tmp.view(heads, dp, C)[:, :d, :])
+        do = torch.empty((Bn, L, HD), dtype=BF16, device=dev)
+        ops.gemm(GEMM_KK, dout, wo, do, M, HD, C, dout.stride(0), C, HD)
+        dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, heads, dp, d ** -0.5)
+        dq2, dk2, dv2 = dq.view(M, HD), dk.view(Mk, HD), dv.view(Mk, HD)
+        xq2, ctx2 = xq.reshape(M, C), ctx.reshape(Mk, Cc)
+        pad_view = ((C, heads, dp), (slice(None), slice(None), slice(0, d)))
+        wgrad(f"{base}/to_q/kernel", xq2, dq2, M, C, (C, HD), pad_view)
+        pad_view_c = ((Cc, heads, dp), (slice(None), slice(None), slice(0, d)))
+        wgrad(f"{base}/to_k/kernel", ctx2, dk2, Mk, Cc, (Cc, HD), pad_view_c)
+        wgrad(f"{base}/to_v/kernel", ctx2, dv2, Mk, Cc, (Cc, HD), pad_view_c)
+        dxq = torch.empty((M, C), dtype=BF16, device=dev)
+        ops.gemm(GEMM_KK, dq2, wq, dxq, M, C, HD, HD, HD, C)
+        dctx = torch.empty((Mk, Cc), dtype=BF16, device=dev)
+        ops.gemm(GEMM_KK, dk2, wk, dctx, Mk, Cc, HD, HD, HD, Cc)
+        ops.gemm(GEMM_KK, dv2, wv, dctx, Mk, Cc, HD, HD, HD, Cc, res=dctx, r_ld=Cc)
+        return dxq, dctx
+
+    @staticmethod
+    def _add2d(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor):
+        """out = a + b on [rows, C] bf16 matrices (libfdx fdx_act_add)."""
+        v = lambda t: t.unsqueeze(0).unsqueeze(0)
+        ops.act_add(v(a), v(b), v(out))
+
+    def _tblock_fwd(self, name, xin: Node, dst: Node, acfg: dict, W, W16, ctx16=None):
+        """TransformerBlock with only_pure_attention=False and / or use_projection=True
+        (models/attention.py:289-303, 321-380):
+            xn = RMSNorm_0(x); px = project_in(xn)
+            h = px + Attention1(norm1(px))                       [use_self_and_cross]
+            h = h + Attention2(norm2(h), textcontext or px)
+            h = h + net_2(GEGLU(net_0.proj(norm3(h))))
+            out = xn + project_out(h)
+        or, with only_pure_attention, out = xn + project_out(Attention2(project_in(xn), context))."""
+        x = xin.t
+        Bn, hh, ww, C = x.shape
+        L, M = hh * ww, Bn * hh * ww
+        heads = acfg["heads"]
+        pure = acfg.get("only_pure_attention", True)
+        proj = acfg.get("use_projection", False)
+        both = acfg.get("use_self_and_cross", True)
+        pre = f"{name}/Attention"
+        dev = x.device
+        xn = ops.rmsnorm_fwd(x, W[f"{name}/RMSNorm_0/scale"], ATTN_EPS)
+        xn2 = xn.view(M, C)
+        px = ops.linear_fwd(xn2, W16[f"{name}/project_in/kernel"]) if proj else xn2
+        ctx = px.view(Bn, L, C) if ctx16 is None else ctx16
+        out2 = dst.t.view(M, C) if dst.t.is_contiguous() else None
+        sv = {"xn": xn, "px": px, "ctx_is_px": ctx16 is None, "ctx": ctx}
+        zeros = None
+
+        def rms(t2, pname):
+            return ops.rmsnorm_fwd(t2.view(Bn, hh, ww, C), W[pname], ATTN_EPS).view(M, C)
+
+        if pure:
+            zeros = torch.zeros((M, C), dtype=BF16, device=dev)
+            h = torch.empty((M, C), dtype=BF16, device=dev)
+            sv["a2"] = self._mha_fwd(f"{pre}/Attention2", px.view(Bn, L, C), ctx, heads, W16, zeros, h)
+        else:
+            h = px
+            if both:
+                n1 = rms(h, f"{pre}/norm1/scale")
+                h1 = torch.empty((M, C), dtype=BF16, device=dev)
+                sv["h0"], sv["a1"] = h, self._mha_fwd(f"{pre}/Attention1", n1.view(Bn, L, C), n1.view(Bn, L, C),
+                                                      heads, W16, h, h1)
+                h = h1
+            n2 = rms(h, f"{pre}/norm2/scale")
+            h2 = torch.empty((M, C), dtype=BF16, device=dev)
+            sv["h1"], sv["a2"] = h, self._mha_fwd(f"{pre}/Attention2", n2.view(Bn, L, C), ctx, heads, W16, h, h2)
+            n3 = rms(h2, f"{pre}/norm3/scale")
+            u = ops.linear_fwd(n3, W16[f"{pre}/ff/net_0/proj/kernel"], bias=W[f"{pre}/ff/net_0/proj/bias"])
+            g = ops.geglu_fwd(u)
+            h3 = ops.linear_fwd(g, W16[f"{pre}/ff/net_2/kernel"], bias=W[f"{pre}/ff/net_2/bias"], res=h2)
+            sv.update(h2=h2, n3=n3, u=u, g=g)
+            h = h3
+        sv["h_last"] = h
+        # out = xn + project_out(h)   (written straight into the destination slot)
+        if proj:
+            ops.gemm(GEMM_KMN, h, W16[f"{name}/project_out/kernel"], dst.t, M, C, C, C, C, dst.t.stride(2),
+                     res=xn, r_ld=C)
+        else:
+            ops.act_add(xn, h.view(Bn, hh, ww, C), dst.t)
+        return ("tblock", name, xin, dst, acfg, sv)
+
+    def _tblock_bwd(self, rec, W, W16, Gd, want, grad_of):
+        _, name, xin, dst, acfg, sv = rec
+        x = xin.t
+        Bn, hh, ww, C = x.shape
+        L, M = hh * ww, Bn * hh * ww
+        pure = acfg.get("only_pure_attention", True)
+        proj = acfg.get("use_projection", False)
+        both = acfg.get("use_self_and_cross", True)
+        pre = f"{name}/Attention"
+        dev = x.device
+        dout = grad_of(dst)                                   # [B,h,w,C], possibly a slot view
+        dout2 = dout.reshape(M, C) if dout.is_contiguous() else dout.contiguous().view(M, C)
+        xn, px = sv["xn"], sv["px"]
+
+        def lin_wgrad(pname, src2, dy2):
+            kin, n = src2.shape[1], dy2.shape[1]
+            ops.gemm(GEMM_MNMN, src2, dy2, Gd[pname], kin, n, src2.shape[0], src2.stride(0), dy2.stride(0), n,
+                     atomic=True, reduce_batch=True)
+
+        def lin_dgrad(dy2, w_kn, out=None, res=None):
+            kin, n = w_kn.shape
+            out = out if out is not None else torch.empty((dy2.shape[0], kin), dtype=BF16, device=dev)
+            ops.gemm(GEMM_KK, dy2, w_kn, out, dy2.shape[0], kin, n, dy2.stride(0), n, kin,
+                     res=res, r_ld=(res.stride(0) if res is not None else 0))
+            return out
+
+        def rms_bwd_into(x2, dy2, pname, dx2):
+            """dx2 += d/dx RMSNorm(x2) given dy2 (accumulates in place)."""
+            v4 = lambda t: t.view(Bn, hh, ww, C)
+            ops.rmsnorm_bwd(v4(x2), v4(dy2), W[pname], ATTN_EPS, v4(dx2), Gd[pname], True)
+
+        # out = xn + project_out(h)
+        if proj:
+            lin_wgrad(f"{name}/project_out/kernel", sv["h_last"], dout2)
+            dh = lin_dgrad(dout2, W16[f"{name}/project_out/kernel"])
+        else:
+            dh = dout2.clone()
+        dctx_px = None
+        if pure:
+            dpx, dctx = self._mha_bwd(sv["a2"], dh, Gd)
+            if sv["ctx_is_px"]:
+                dctx_px = dctx
+        else:
+            # h3 = h2 + net_2(g)
+            g, u, n3, h2 = sv["g"], sv["u"], sv["n3"], sv["h2"]
+            lin_wgrad(f"{pre}/ff/net_2/kernel", g, dh)
+            ops.colsum_rows(dh, Gd[f"{pre}/ff/net_2/bias"])
+            dg = lin_dgrad(dh, W16[f"{pre}/ff/net_2/kernel"])
+            du = ops.geglu_bwd(u, dg)
+            lin_wgrad(f"{pre}/ff/net_0/proj/kernel", n3, du)
+            ops.colsum_rows(du, Gd[f"{pre}/ff/net_0/proj/bias"])
+            dn3 = lin_dgrad(du, W16[f"{pre}/ff/net_0/proj/kernel"])
+            rms_bwd_into(h2, dn3, f"{pre}/norm3/scale", dh)            # dh = d h2
+            # h2 = h1 + Attention2(norm2(h1), ctx)
+            dn2, dctx = self._mha_bwd(sv["a2"], dh, Gd)
+            if sv["ctx_is_px"]:
+                dctx_px = dctx
+            rms_bwd_into(sv["h1"], dn2, f"{pre}/norm2/scale", dh)      # dh = d h1
+            if both:
+                # h1 = h0 + Attention1(norm1(h0)) with keys / values from the same normed tensor
+                dn1, dkv1 = self._mha_bwd(sv["a1"], dh, Gd)
+                self._add2d(dn1, dkv1, dn1)
+                rms_bwd_into(sv["h0"], dn1, f"{pre}/norm1/scale", dh)  # dh = d h0 = d px
+            dpx = dh
+        if dctx_px is not None:                                        # context = px (textcontext is None)
+            self._add2d(dpx, dctx_px, dpx)
+        # px = project_in(xn);  d xn = dout (residual) + d px . W_in^T
+        dxn = torch.empty((M, C), dtype=BF16, device=dev)
+        if proj:
+            lin_wgrad(f"{name}/project_in/kernel", xn.view(M, C), dpx)
+            lin_dgrad(dpx, W16[f"{name}/project_in/kernel"], out=dxn, res=dout2)
+        else:
+            self._add2d(dpx, dout2, dxn)
+        dx, acc = want(xin)
+        ops.rmsnorm_bwd(x, dxn.view(Bn, hh, ww, C), W[f"{name}/RMSNorm_0/scale"], ATTN_EPS, dx,
+                        Gd[f"{name}/RMSNorm_0/scale"], acc)
+
     # ------------------------------------------------------------------ backward program
     def backward(self, fp: FlatParams, saved: dict, dF: torch.Tensor, grads: FlatParams, on_ready=None):
         """Accumulates d(loss)/d(params) into `grads` (f32, caller zeroes it) given dF = dL/dF.
@@ -635,6 +881,8 @@ class Unet:
                 self._attn_bwd(rec, W, W16, Gd, want, grad_of)
             elif kind == "attn_unfused":
                 self._attn_bwd_unfused(rec, W, W16, Gd, want, grad_of)
+            elif kind == "tblock":
+                self._tblock_bwd(rec, W, W16, Gd, want, grad_of)
             elif kind == "conv":
                 _, _, xin, dst = rec
                 dy = grad_of(dst)

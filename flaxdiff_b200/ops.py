@@ -591,6 +591,36 @@ def conv_out_wgrad_direct(x, dF, dw, dbias):
                                     stream_ptr()), "conv_out_wgrad")
 
 
+# --------------------------------------------------------------------------- GEGLU
+def geglu_fwd(u: torch.Tensor) -> torch.Tensor:
+    """u [rows, 2*inner] bf16 -> hidden_linear * gelu_tanh(hidden_gelu) [rows, inner]."""
+    rows, two = u.shape
+    assert u.dtype == torch.bfloat16 and u.is_contiguous() and two % 16 == 0
+    g = torch.empty((rows, two // 2), dtype=torch.bfloat16, device=u.device)
+    check(load().fdx_geglu_fwd(ptr(u), ctypes.c_longlong(rows), ctypes.c_int(two // 2), ptr(g), stream_ptr()),
+          "geglu_fwd")
+    return g
+
+
+def geglu_bwd(u: torch.Tensor, dg: torch.Tensor) -> torch.Tensor:
+    rows, two = u.shape
+    assert dg.shape == (rows, two // 2) and dg.is_contiguous() and dg.dtype == torch.bfloat16
+    du = torch.empty_like(u)
+    check(load().fdx_geglu_bwd(ptr(u), ptr(dg), ctypes.c_longlong(rows), ctypes.c_int(two // 2), ptr(du),
+                               stream_ptr()), "geglu_bwd")
+    return du
+
+
+def colsum_rows(x2d: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[c] = sum over rows of x2d[:, c] (bias gradients of dense layers); columns in slabs of <= 2048."""
+    rows, n = x2d.shape
+    assert x2d.stride(1) == 1 and out.numel() == n
+    for c0 in range(0, n, 2048):
+        c1 = min(n, c0 + 2048)
+        colsum(x2d[:, c0:c1].unsqueeze(0).unsqueeze(0), False, out=out[c0:c1])
+    return out
+
+
 # --------------------------------------------------------------------------- fused attention
 def _attn_desc(q, k, v, o, lse, heads: int, dh: int, scale: float):
     """q / o: [B, L, heads*dh], k / v: [B, Lk, heads*dh] (bf16, last dim contiguous)."""

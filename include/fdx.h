@@ -274,6 +274,13 @@ int fdx_softmax_fwd(const float* S, long long rows, int L, int Lp, void* P_bf16,
 int fdx_softmax_bwd(const void* P_bf16, const float* dP, long long rows, int L, int Lp, float scale,
                     void* dS_bf16, void* stream);
 
+/* FlaxGEGLU of the full transformer block (models/attention.py:179-205): u bf16 [rows][2*inner] =
+ * [hidden_linear | hidden_gelu] -> g = hidden_linear * gelu_tanh(hidden_gelu) bf16 [rows][inner], and its
+ * backward du [rows][2*inner] from dg.  inner a multiple of 8. */
+int fdx_geglu_fwd(const void* u_bf16, long long rows, int inner, void* g_bf16, void* stream);
+int fdx_geglu_bwd(const void* u_bf16, const void* dg_bf16, long long rows, int inner, void* du_bf16,
+                  void* stream);
+
 /* ---- fused attention (fdx_attn.cu) ------------------------------------------------------------------
  * nn.dot_product_attention inside NormalAttention (models/attention.py:156-177): o = softmax(q k^T * scale) v
  * per (image, head), self-attention (Lk = L) or cross-attention to the text context (Lk = 77), and its

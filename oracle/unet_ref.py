@@ -116,6 +116,52 @@ def attention_block(P, name, x, heads, context=None, eps=1e-4):
     return xn + proj
 
 
+def _mha(P, base, xq, ctx, heads):
+    """NormalAttention (attention.py:117-177) on (B, L, C) tokens."""
+    d = xq.shape[-1] // heads
+    q = torch.einsum("blc,chd->blhd", xq, P[f"{base}/to_q/kernel"])
+    k = torch.einsum("bkc,chd->bkhd", ctx, P[f"{base}/to_k/kernel"])
+    v = torch.einsum("bkc,chd->bkhd", ctx, P[f"{base}/to_v/kernel"])
+    w = torch.softmax(torch.einsum("blhd,bkhd->bhlk", q / math.sqrt(d), k), dim=-1)
+    o = torch.einsum("bhlk,bkhd->blhd", w, v)
+    return torch.einsum("blhd,hdc->blc", o, P[f"{base}/to_out_0/kernel"])
+
+
+def transformer_block(P, name, x, acfg, context=None, eps=1e-4):
+    """TransformerBlock + BasicTransformerBlock + FlaxFeedForward / FlaxGEGLU in full generality
+    (attention.py:179-303, 305-380): input RMSNorm, optional Dense project_in / project_out (no bias),
+    self-attention (Attention1), cross-attention (Attention2; context = projected x when none is given),
+    GEGLU feed-forward, residual on the NORMALISED input."""
+    B, H, W, C = x.shape
+    heads = acfg["heads"]
+    xn = rms_norm(x, P[f"{name}/RMSNorm_0/scale"], eps)
+    t = xn.reshape(B, H * W, C)
+    proj = acfg.get("use_projection", False)
+    px = t @ P[f"{name}/project_in/kernel"] if proj else t
+    ctx = px if context is None else context
+    pre = f"{name}/Attention"
+    if acfg.get("only_pure_attention", True):
+        h = _mha(P, f"{pre}/Attention2", px, ctx, heads)
+    else:
+        h = px
+        if acfg.get("use_self_and_cross", True):
+            n1 = rms_norm(h, P[f"{pre}/norm1/scale"], eps)
+            h = h + _mha(P, f"{pre}/Attention1", n1, n1, heads)
+        h = h + _mha(P, f"{pre}/Attention2", rms_norm(h, P[f"{pre}/norm2/scale"], eps), ctx, heads)
+        u = rms_norm(h, P[f"{pre}/norm3/scale"], eps) @ P[f"{pre}/ff/net_0/proj/kernel"] + P[f"{pre}/ff/net_0/proj/bias"]
+        lin, gate = torch.chunk(u, 2, dim=-1)
+        h = h + (lin * gelu_tanh(gate)) @ P[f"{pre}/ff/net_2/kernel"] + P[f"{pre}/ff/net_2/bias"]
+    if proj:
+        h = h @ P[f"{name}/project_out/kernel"]
+    return xn + h.reshape(B, H, W, C)
+
+
+def _attn(P, name, x, acfg, context):
+    if acfg.get("only_pure_attention", True) and not acfg.get("use_projection", False):
+        return attention_block(P, name, x, acfg["heads"], context)
+    return transformer_block(P, name, x, acfg, context)
+
+
 def unet_forward(P: Dict[str, torch.Tensor], x, t, freqs, feature_depths: Sequence[int] = (64, 128, 256, 512),
                  attention_configs=(None, None, None, None), num_res_blocks=2, num_middle_res_blocks=1,
                  norm_groups=8, textcontext=None, named_norms=False):
@@ -130,7 +176,7 @@ def unet_forward(P: Dict[str, torch.Tensor], x, t, freqs, feature_depths: Sequen
         for j in range(num_res_blocks):
             x = residual_block(P, f"down_{i}_residual_{j}", x, temb, norm_groups, n1, n2)
             if acfg is not None and j == num_res_blocks - 1:
-                x = attention_block(P, f"down_{i}_attention_{j}", x, acfg["heads"], textcontext)
+                x = _attn(P, f"down_{i}_attention_{j}", x, acfg, textcontext)
             downs.append(x)
         if i != L - 1:
             x = conv_same(x, P[f"down_{i}_downsample/ConvLayer_0/conv/kernel"],
@@ -139,14 +185,14 @@ def unet_forward(P: Dict[str, torch.Tensor], x, t, freqs, feature_depths: Sequen
     for j in range(num_middle_res_blocks):
         x = residual_block(P, f"middle_res1_{j}", x, temb, norm_groups, n1, n2)
         if macfg is not None and j == num_middle_res_blocks - 1:
-            x = attention_block(P, f"middle_attention_{j}", x, macfg["heads"], textcontext)
+            x = _attn(P, f"middle_attention_{j}", x, macfg, textcontext)
         x = residual_block(P, f"middle_res2_{j}", x, temb, norm_groups, n1, n2)
     for i, (dim_out, acfg) in enumerate(zip(reversed(feature_depths), reversed(attention_configs))):
         for j in range(num_res_blocks):
             x = torch.cat([x, downs.pop()], dim=-1)
             x = residual_block(P, f"up_{i}_residual_{j}", x, temb, norm_groups, n1, n2)
             if acfg is not None and j == num_res_blocks - 1:
-                x = attention_block(P, f"up_{i}_attention_{j}", x, acfg["heads"], textcontext)
+                x = _attn(P, f"up_{i}_attention_{j}", x, acfg, textcontext)
         if i != L - 1:
             x = x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)   # jax.image.resize nearest x2
             x = conv_same(x, P[f"up_{i}_upsample/ConvLayer_0/conv/kernel"],

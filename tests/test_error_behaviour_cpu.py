@@ -14,8 +14,10 @@ from flaxdiff_b200.trainer import GeneralDiffusionTrainer, adamw
 
 @pytest.mark.parametrize("kw,needle", [
     (dict(norm_groups=0), "norm_groups"),
-    (dict(attention_configs=(None, None, None, {"heads": 8, "use_projection": True})), "use_projection"),
-    (dict(attention_configs=(None, None, None, {"heads": 8, "only_pure_attention": False})), "only_pure_attention"),
+    (dict(attention_configs=(None, None, None, {"heads": 8, "flash_attention": True})), "flash_attention"),
+    (dict(attention_configs=(None, None, None, {"heads": 8, "norm_inputs": False})), "norm_inputs"),
+    (dict(attention_configs=(None, None, None, {"heads": 8, "only_pure_attention": False,
+                                                "explicitly_add_residual": False})), "explicitly_add_residual"),
     (dict(attention_configs=(None, None, None)), "one entry per level"),
     (dict(output_channels=4), "output_channels"),
     (dict(dtype=torch.float16), "dtype"),
@@ -35,10 +37,21 @@ def test_unet_accepts_the_reference_defaults_and_swish_callables():
     def swish(x):
         return x
     Unet(attention_configs=(None,) * 4, activation=swish)    # jax.nn.swish is a function named "swish"
+    # the full transformer block and the projections are supported (SURVEY $8 f3)
+    m = Unet(attention_configs=(None, None, None, {"heads": 8, "only_pure_attention": False, "use_projection": True}),
+             context_dim=768)
+    names = [n for n, _ in m.param_specs()]
+    for leaf in ("project_in/kernel", "Attention/Attention1/to_q/kernel", "Attention/Attention2/to_k/kernel",
+                 "Attention/ff/net_0/proj/kernel", "Attention/ff/net_0/proj/bias", "Attention/ff/net_2/kernel",
+                 "Attention/norm1/scale", "Attention/norm3/scale", "project_out/kernel"):
+        assert f"middle_attention_0/{leaf}" in names, leaf
+    lay = dict(m.param_specs())
+    assert lay["middle_attention_0/Attention/ff/net_0/proj/kernel"] == (512, 4096)       # dim -> 2 * 4 * dim
+    assert lay["middle_attention_0/Attention/ff/net_2/kernel"] == (2048, 512)
+    assert lay["middle_attention_0/Attention/Attention2/to_k/kernel"] == (768, 8, 64)
 
 
-@pytest.mark.parametrize("kw,needle", [(dict(autoencoder=object()), "autoencoder"),
-                                       (dict(use_dynamic_scale=True), "DynamicScale")])
+@pytest.mark.parametrize("kw,needle", [(dict(autoencoder=object()), "autoencoder")])
 def test_trainer_rejects_unsupported_options(kw, needle):
     with pytest.raises(FdxError, match=needle):
         GeneralDiffusionTrainer(Unet(attention_configs=(None,) * 4), adamw(1e-3), EDMNoiseScheduler(1),

@@ -316,3 +316,51 @@ def test_cfg_euler_ancestral_sampling_vs_oracle(monkeypatch):
         one = np.ones(B, np.float32)
         x = torch.from_numpy(R.euler_ancestral_step(x.numpy(), x0.numpy(), noises[i].numpy(), one, sig, one, ns))
     assert rel(out, x) < 6e-2
+
+
+FULL_BLOCKS = [
+    # (attention config, context_dim)
+    ({"heads": 8, "only_pure_attention": False}, None),                                  # self + "cross to itself" + FF
+    ({"heads": 8, "only_pure_attention": False, "use_projection": True}, 768),           # the full text block
+    ({"heads": 8, "only_pure_attention": False, "use_self_and_cross": False}, 768),      # cross + FF only
+    ({"heads": 8, "only_pure_attention": True, "use_projection": True}, None),           # projections around pure attention
+]
+
+
+@pytest.mark.parametrize("cfg,ctxdim", FULL_BLOCKS)
+def test_full_transformer_block_forward_backward_vs_oracle(cfg, ctxdim):
+    """SURVEY $8 f3: only_pure_attention=False (self-attention + cross-attention + GEGLU feed-forward) and
+    use_projection=True (models/attention.py:179-303, 327-374) at the 8x8 (C=512, d=64) and 16x16 (C=256,
+    d=32) levels of a 64x64 UNet, against the oracle restatement."""
+    torch.manual_seed(0)
+    levels = (None, None, cfg, cfg)
+    model = Unet(attention_configs=levels, dtype=torch.bfloat16, context_dim=ctxdim)
+    fp = model.init(4, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2)
+    for name, t in fp.named.items():           # non-trivial norm scales and feed-forward biases
+        if name.endswith("scale"):
+            t.copy_(1 + 0.1 * torch.randn(t.shape, generator=g, device=dev))
+        elif name.endswith("bias"):
+            t.copy_(0.05 * torch.randn(t.shape, generator=g, device=dev))
+    fp.touch()
+    B, res = 2, 64
+    x = torch.randn(B, res, res, 3, device=dev).bfloat16()
+    t = torch.randn(B, device=dev)
+    ctx = torch.randn(B, 77, 768, device=dev).bfloat16() if ctxdim else None
+    F, saved = model.forward(fp, x, t, ctx, save=True)
+    P = cpu_params(fp, True)
+    Fr = unet_ref.unet_forward(P, x.float().cpu(), t.cpu(), model._fourier_freqs(dev).cpu(), attention_configs=levels,
+                               textcontext=None if ctx is None else ctx.float().cpu())
+    assert rel(F, Fr) < 3e-2, rel(F, Fr)
+    dF = torch.randn(B, res, res, 3, device=dev) / (B * res * res * 3)
+    grads = fp.zeros_like()
+    model.backward(fp, saved, dF, grads)
+    (Fr * dF.cpu()).sum().backward()
+    num = den = 0.0
+    for k in P:
+        gg, gr = grads.named[k].cpu(), P[k].grad
+        assert rel(gg, gr) < 8e-2, (k, rel(gg, gr))
+        num += (gg - gr).pow(2).sum().item()
+        den += gr.pow(2).sum().item()
+    assert (num / den) ** 0.5 < 3e-2
