@@ -470,6 +470,220 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
   }
 }
 
+// ---- GroupNorm(+SiLU) backward in ONE launch: a thread-block CLUSTER per image ------------------------
+// The two-pass backward above reads x and dy twice from HBM (8 B + 2 B written per element).  The
+// statistics it needs are per IMAGE, so here a cluster of CL CTAs owns one image: every CTA runs pass 1 on
+// its slice of the pixels, the per-channel sums are exchanged through distributed shared memory
+// (mapa + ld.shared::cluster), every CTA derives the per-group constants, and pass 2 re-reads the SAME
+// slice - a few hundred microseconds later at most, while the lines are still in the 126 MB L2 (the launch
+// keeps the images in flight, 148 / CL clusters, below ~48 MB of x + dy).  HBM traffic: 4 B read + 2 B
+// written per element.  ws[n][c] = (S0, S1) is still written (rank 0) for the dgamma / dbeta finalize.
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+template <bool SILU, bool ACC, bool CS>
+__global__ void __launch_bounds__(kNT, 2)
+gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
+                      const __nv_bfloat16* __restrict__ dy, long long dps, int HW, int C, int G,
+                      const float* __restrict__ stats, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, float* __restrict__ ws,
+                      __nv_bfloat16* __restrict__ dx, long long dxps, float* __restrict__ csum_img) {
+  const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
+  const uint32_t CL = cluster_nctarank(), rank = cluster_ctarank();
+  const int n = blockIdx.x / CL;
+  const int tid = threadIdx.x;
+  extern __shared__ float shm[];
+  float* part0 = shm;                      // [rows*C]   pass-1 partials / pass-2 column sums
+  float* part1 = part0 + rows * C;         // [rows*C]
+  float* tot = part1 + rows * C;           // [2*C]  this CTA's per-channel sums (read by the peers)
+  float* redg = tot + 2 * C;               // [2*G]
+  const float cnt = (float)HW * (float)cpg;
+  const int p_lo = (int)(((long long)HW * rank) / CL), p_hi = (int)(((long long)HW * (rank + 1)) / CL);
+  const bool active = tid < rows * vpp;
+  const int cv = tid % vpp, r = tid / vpp;
+  const int g = (cv * 8) / cpg;
+  float mean = 0.f, rstd = 0.f;
+  GnPair4 ah, bh;
+  const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
+  const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
+  if (active) {
+    mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
+    const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+    rstd = rsqrtf(var + eps);
+    GnPair4 s0, s1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a0 = rstd * gamma[cv * 8 + 2 * j], a1 = rstd * gamma[cv * 8 + 2 * j + 1];
+      ah.v[j] = f2_pack(0.5f * a0, 0.5f * a1);
+      bh.v[j] = SILU ? f2_pack(0.5f * (beta[cv * 8 + 2 * j] - mean * a0), 0.5f * (beta[cv * 8 + 2 * j + 1] - mean * a1))
+                     : f2_pack(0.f, 0.f);
+      s0.v[j] = f2_pack(0.f, 0.f);
+      s1.v[j] = f2_pack(0.f, 0.f);
+    }
+    for (int p0 = p_lo + r; p0 < p_hi; p0 += kBU * rows) {
+      uint4 xu[kBU], du[kBU];
+#pragma unroll
+      for (int k = 0; k < kBU; ++k) {
+        const int p = p0 + k * rows;
+        xu[k] = make_uint4(0, 0, 0, 0);
+        du[k] = make_uint4(0, 0, 0, 0);
+        if (p < p_hi) {
+          xu[k] = *reinterpret_cast<const uint4*>(xb + (long long)p * xps);
+          du[k] = *reinterpret_cast<const uint4*>(db_ + (long long)p * dps);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kBU; ++k) {
+        const uint32_t xw[4] = {xu[k].x, xu[k].y, xu[k].z, xu[k].w};
+        const uint32_t dw[4] = {du[k].x, du[k].y, du[k].z, du[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const f32x2_t xv = f2_from_bf16x2(xw[j]);
+          const f32x2_t dz = gn_dz_pair<SILU, false>(xv, f2_from_bf16x2(dw[j]), ah.v[j], bh.v[j]);
+          s0.v[j] = f2_add(s0.v[j], dz);
+          s1.v[j] = f2_fma(dz, xv, s1.v[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo, hi;
+      f2_unpack(s0.v[j], lo, hi);
+      part0[r * C + cv * 8 + 2 * j] = lo; part0[r * C + cv * 8 + 2 * j + 1] = hi;
+      f2_unpack(s1.v[j], lo, hi);
+      part1[r * C + cv * 8 + 2 * j] = lo; part1[r * C + cv * 8 + 2 * j + 1] = hi;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kNT) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int rr = 0; rr < rows; ++rr) { t0 += part0[rr * C + c]; t1 += part1[rr * C + c]; }
+    tot[c] = t0;
+    tot[C + c] = t1;
+  }
+  cluster_sync_all();                       // every CTA's `tot` is complete and visible cluster-wide
+  if (tid < 2 * G) redg[tid] = 0.f;
+  __syncthreads();
+  for (int c = tid; c < C; c += kNT) {
+    float S0 = 0.f, S1 = 0.f;
+    for (uint32_t k = 0; k < CL; ++k) { S0 += ld_dsmem_f32(tot + c, k); S1 += ld_dsmem_f32(tot + C + c, k); }
+    if (rank == 0) {
+      ws[((long long)n * C + c) * 2] = S0;
+      ws[((long long)n * C + c) * 2 + 1] = S1;
+    }
+    const int gc = c / cpg;
+    const float mg = stats[(long long)n * 2 * G + 2 * gc] / cnt;
+    const float vg = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * gc + 1] / cnt - mg * mg);
+    const float rg = rsqrtf(vg + eps), ga = gamma[c];
+    atomicAdd(&redg[2 * gc], ga * S0);
+    atomicAdd(&redg[2 * gc + 1], ga * rg * (S1 - mg * S0));
+  }
+  cluster_sync_all();                       // peers are done reading this CTA's `tot`; redg complete
+  // ---- pass 2 on the same pixel slice (L2-resident) ----
+  if (active) {
+    const float m1 = redg[2 * g] / cnt, m2 = redg[2 * g + 1] / cnt;
+    const float c2 = rstd * rstd * m2;
+    const float c3 = mean * c2 - rstd * m1;
+    const f32x2_t nc2 = f2_pack(-c2, -c2), c3p = f2_pack(c3, c3);
+    GnPair4 cs;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cs.v[j] = f2_pack(0.f, 0.f);
+    __nv_bfloat16* ob = dx + (long long)n * HW * dxps + cv * 8;
+    for (int p0 = p_lo + r; p0 < p_hi; p0 += kBU * rows) {
+      uint4 xu[kBU], du[kBU], ou[kBU];
+#pragma unroll
+      for (int k = 0; k < kBU; ++k) {
+        const int p = p0 + k * rows;
+        xu[k] = make_uint4(0, 0, 0, 0);
+        du[k] = make_uint4(0, 0, 0, 0);
+        ou[k] = make_uint4(0, 0, 0, 0);
+        if (p < p_hi) {
+          xu[k] = *reinterpret_cast<const uint4*>(xb + (long long)p * xps);
+          du[k] = *reinterpret_cast<const uint4*>(db_ + (long long)p * dps);
+          if (ACC) ou[k] = *reinterpret_cast<const uint4*>(ob + (long long)p * dxps);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kBU; ++k) {
+        const int p = p0 + k * rows;
+        if (p < p_hi) {
+          const uint32_t xw[4] = {xu[k].x, xu[k].y, xu[k].z, xu[k].w};
+          const uint32_t dw[4] = {du[k].x, du[k].y, du[k].z, du[k].w};
+          const uint32_t ow[4] = {ou[k].x, ou[k].y, ou[k].z, ou[k].w};
+          uint32_t res[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const f32x2_t xv = f2_from_bf16x2(xw[j]);
+            const f32x2_t dz2 = gn_dz_pair<SILU, true>(xv, f2_from_bf16x2(dw[j]), ah.v[j], bh.v[j]);
+            f32x2_t v = f2_fma(dz2, ah.v[j], f2_fma(xv, nc2, c3p));
+            if (CS) cs.v[j] = f2_add(cs.v[j], v);
+            if (ACC) v = f2_add(v, f2_from_bf16x2(ow[j]));
+            res[j] = f2_to_bf16x2(v);
+          }
+          *reinterpret_cast<uint4*>(ob + (long long)p * dxps) = make_uint4(res[0], res[1], res[2], res[3]);
+        }
+      }
+    }
+    if (CS) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float lo, hi;
+        f2_unpack(cs.v[j], lo, hi);
+        part0[r * C + cv * 8 + 2 * j] = lo;
+        part0[r * C + cv * 8 + 2 * j + 1] = hi;
+      }
+    }
+  }
+  if (CS) {
+    __syncthreads();
+    for (int c = tid; c < C; c += kNT) {
+      float v = 0.f;
+      for (int rr = 0; rr < rows; ++rr) v += part0[rr * C + c];
+      atomicAdd(&csum_img[(long long)n * C + c], v);
+    }
+  }
+}
+
+template <bool SILU, bool ACC, bool CS>
+int launch_bwd_cluster(int CL, size_t shm, const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
+                       const float* gamma, const float* beta, float eps, float* ws, const fdx_act* dx,
+                       float* csum_img, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FDX_CUDA(cudaFuncSetAttribute(gn_bwd_cluster_kernel<SILU, ACC, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  200 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(x->n * CL));
+  cfg.blockDim = dim3(kNT);
+  cfg.dynamicSmemBytes = shm;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FDX_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_cluster_kernel<SILU, ACC, CS>, (const __nv_bfloat16*)x->ptr,
+                              (long long)x->pix_stride, (const __nv_bfloat16*)dy->ptr, (long long)dy->pix_stride,
+                              x->h * x->w, x->c, groups, stats, gamma, beta, eps, ws, (__nv_bfloat16*)dx->ptr,
+                              (long long)dx->pix_stride, csum_img));
+  fdx_count_launch();
+  return FDX_OK;
+}
+
 // ---------------------------------------------------------------------------
 // RMSNorm over channels, one warp per pixel.
 // ---------------------------------------------------------------------------
@@ -689,6 +903,49 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
   const int N = x->n, C = x->c, HW = x->h * x->w;
   float* sums = ws;                         // [N][C][2]
   float* red = ws + 2LL * N * C;            // [N][G][2]
+  // One-launch cluster path (x and dy read from HBM once): images of >= 1024 pixels.  The cluster size sets
+  // both the parallelism per image and - with the shared-memory request that limits residency - how many
+  // images are in flight; their x + dy must stay well inside the L2.  FDX_GN_2PASS=1 keeps the two-pass path.
+  static const bool two_pass = getenv("FDX_GN_2PASS") != nullptr;
+  const double img_bytes = 4.0 * HW * C;                      // x + dy of one image, bf16
+  int CL = 8;
+  while (CL > 1 && (HW / CL) < 4 * (kNT / (C / 8))) CL >>= 1;  // keep >= 4 row iterations per CTA
+  // images in flight with one CTA per SM = 148 / CL; beyond ~64 MB the second pass would miss in L2 anyway
+  const bool fits_l2 = (148.0 / CL) * img_bytes <= 64.0 * 1024 * 1024;
+  if (!two_pass && HW >= 1024 && fits_l2) {
+    // CTAs per SM so that (148 * per_sm / CL) images * img_bytes <= 48 MB, at least 1
+    int per_sm = (int)((48.0 * 1024 * 1024 * CL) / (148.0 * img_bytes));
+    if (per_sm > 2) per_sm = 2;
+    if (per_sm < 1) per_sm = 1;
+    const size_t need = sizeof(float) * (2 * (size_t)(kNT / (C / 8)) * C + 2 * C + 2 * groups);
+    size_t shm = need;
+    const size_t force = per_sm == 1 ? 120 * 1024 : 0;       // > half of the SM's shared memory => one CTA / SM
+    if (shm < force) shm = force;
+    if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * N * C, st));
+    const int key = (silu ? 4 : 0) | (accumulate ? 2 : 0) | (csum_img ? 1 : 0);
+    int rc;
+#define FDX_GN_CL(S, A, CSF) rc = launch_bwd_cluster<S, A, CSF>(CL, shm, x, dy, groups, stats, gamma, beta, eps, sums, dx, csum_img, st)
+    switch (key) {
+      case 0: FDX_GN_CL(false, false, false); break;
+      case 1: FDX_GN_CL(false, false, true); break;
+      case 2: FDX_GN_CL(false, true, false); break;
+      case 3: FDX_GN_CL(false, true, true); break;
+      case 4: FDX_GN_CL(true, false, false); break;
+      case 5: FDX_GN_CL(true, false, true); break;
+      case 6: FDX_GN_CL(true, true, false); break;
+      default: FDX_GN_CL(true, true, true); break;
+    }
+#undef FDX_GN_CL
+    if (rc != FDX_OK) return rc;
+    const int cb = (C + kFinC - 1) / kFinC;
+    gn_bwd_finalize_kernel<<<cb, 256, 0, st>>>(sums, stats, gamma, N, HW, C, groups, eps, cb, red, dgamma, dbeta);
+    FDX_LAUNCH_CHECK();
+    if (csum_tot) {
+      reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(csum_img, N, C, csum_tot, 0);
+      FDX_LAUNCH_CHECK();
+    }
+    return FDX_OK;
+  }
   FDX_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, st));
   const size_t shm = sizeof(float) * 2 * (kNT / (C / 8)) * C;
   if (silu)
