@@ -56,11 +56,15 @@ class _GraphedEval:
         with torch.cuda.graph(self.graph):
             self.static_out = fn(*self.static_in)
 
-    def __call__(self, *inputs):
+    def __call__(self, *inputs, clone: bool = True):
         for s, t in zip(self.static_in, inputs):
-            s.copy_(t)
+            if s.data_ptr() != t.data_ptr():
+                s.copy_(t)
         self.graph.replay()
-        return tuple(o.clone() for o in self.static_out)
+        if not clone:                        # valid until the next replay (stream-ordered consumers only)
+            return self.static_out if isinstance(self.static_out, tuple) else (self.static_out,)
+        outs = self.static_out if isinstance(self.static_out, tuple) else (self.static_out,)
+        return tuple(o.clone() for o in outs)
 
 
 class DiffusionSampler:
@@ -117,6 +121,12 @@ class DiffusionSampler:
         x0, eps = _affine([x_t, Fm], [p, q], [r, u])
         return x0, eps, Fm
 
+    # Deterministic single-launch update rules (Euler, Heun, DDIM eta=0, ...) set this: generate_samples then
+    # captures the WHOLE step - model evaluation(s) + the (B,)-sized coefficient algebra + the update kernel -
+    # in one CUDA graph with (x, current_step, next_step) as inputs, so a denoise step is one replay instead
+    # of a replay plus ~30 tiny un-graphed launches (the reference runs them as un-jitted XLA dispatches,
+    # SURVEY.md $3.2).  Samplers that draw noise or keep Python-side history use the per-evaluation graph.
+    _whole_step_graph = False
     MAX_GRAPHS = 4      # captured graphs kept per sampler (each owns a private memory pool)
     MAX_TREES = 2       # flax-tree -> FlatParams conversions kept per sampler
 
@@ -143,8 +153,8 @@ class DiffusionSampler:
         if t.dim() == 0:
             t = t.expand(x_t.shape[0])
         t = t.contiguous()
-        if not self.use_cuda_graph:
-            return self._eval(fp, x_t, t, *conditioning_inputs)
+        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
+            return self._eval(fp, x_t, t, *conditioning_inputs)      # (inside a whole-step capture: inline)
         # The graph reads the parameters through fp's bf16 shadow / f32 buffers BY POINTER, so new parameter
         # VALUES (training steps, EMA updates, checkpoint loads) need no re-capture: the shadow is re-cast
         # here when fp's generation moved (FlatParams.gen - torch's version counter does not see libfdx
@@ -161,6 +171,25 @@ class DiffusionSampler:
         else:
             self._graphs.move_to_end(key)
         return ge(x_t, t, *conditioning_inputs)
+
+    def _graphed_step(self, fp, x, cur, nxt, conds):
+        """One full sampler step through a captured graph (see _whole_step_graph)."""
+        key = ("step", id(fp), tuple(x.shape), tuple((tuple(c.shape), c.dtype) for c in conds))
+        ge = self._graphs.get(key)
+        fp.shadow()
+        if ge is None:
+            def fn(a, c, n, *cc):
+                def smf(x_t, t, *add):
+                    return self.sample_model(fp, x_t, t, *add)
+                out, _ = self.sample_step(smf, a, c, list(cc), next_step=n, state=None)
+                return out
+            ge = _GraphedEval(fn, [x, cur, nxt, *conds])
+            self._graphs[key] = ge
+            while len(self._graphs) > self.MAX_GRAPHS:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
+        return ge(x, cur, nxt, *conds, clone=False)[0]
 
     def post_process(self, samples: torch.Tensor) -> torch.Tensor:
         ones = torch.ones((1, samples.shape[0]), dtype=torch.float32, device=samples.device)
@@ -249,10 +278,17 @@ class DiffusionSampler:
         steps = steps_override if steps_override is not None else self.get_steps(start_step, end_step, diffusion_steps)
         steps = [float(s) for s in np.asarray(steps).tolist()]
         n = len(steps)
+        whole = self.use_cuda_graph and self._whole_step_graph and n > 1
+        if whole:
+            # per-step (B,) step tensors, built once: rows are views, no per-step fill kernels
+            tab = torch.tensor([self.scale_steps(s) for s in steps] + [self.scale_steps(0)], dtype=torch.float32,
+                               device=device).unsqueeze(1).expand(n + 1, samples.shape[0]).contiguous()
         for i in range(n):
             current_step = self.scale_steps(steps[i])
             next_step = self.scale_steps(steps[i + 1] if i + 1 < n else 0)
-            if i != n - 1:
+            if i != n - 1 and whole:
+                samples = self._graphed_step(params, samples, tab[i], tab[i + 1], tuple(model_conditioning_inputs))
+            elif i != n - 1:
                 samples, rngstate = self.sample_step(sample_model_fn, samples, current_step,
                                                      model_conditioning_inputs, next_step=next_step, state=rngstate)
             else:

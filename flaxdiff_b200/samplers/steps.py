@@ -27,6 +27,8 @@ def _rates(schedule, step):
 
 
 class EulerSampler(DiffusionSampler):
+    _whole_step_graph = True
+
     def take_next_step(self, current_samples, reconstructed_samples, model_conditioning_inputs, pred_noise,
                        current_step, state: RandomMarkovState, sample_model_fn, next_step=1):
         ca, cs = _rates(self.noise_schedule, current_step)
@@ -39,6 +41,8 @@ class EulerSampler(DiffusionSampler):
 
 
 class SimplifiedEulerSampler(DiffusionSampler):
+    _whole_step_graph = True
+
     def take_next_step(self, current_samples, reconstructed_samples, model_conditioning_inputs, pred_noise,
                        current_step, state: RandomMarkovState, sample_model_fn, next_step=1):
         _, cs = _rates(self.noise_schedule, current_step)
@@ -63,6 +67,8 @@ class EulerAncestralSampler(DiffusionSampler):
 
 
 class HeunSampler(DiffusionSampler):
+    _whole_step_graph = True
+
     def take_next_step(self, current_samples, reconstructed_samples, model_conditioning_inputs, pred_noise,
                        current_step, state: RandomMarkovState, sample_model_fn, next_step=1):
         ca, cs = _rates(self.noise_schedule, current_step)
@@ -82,6 +88,7 @@ class DDIMSampler(DiffusionSampler):
     def __init__(self, *args, eta=0.0, **kwargs):
         super().__init__(*args, **kwargs)
         self.eta = eta
+        self._whole_step_graph = (eta == 0)      # eta > 0 draws noise per step
 
     def take_next_step(self, current_samples, reconstructed_samples, model_conditioning_inputs, pred_noise,
                        current_step, state: RandomMarkovState, sample_model_fn, next_step=1):
