@@ -43,6 +43,14 @@ OUT_EPS = 1e-6      # flax GroupNorm default epsilon for Unet.conv_out_norm (sim
 ATTN_EPS = 1e-4     # TransformerBlock.norm_epsilon, models/attention.py:319
 
 
+def _attn_width(d: int) -> int:
+    """Stored head width for the fused attention kernels: 32 or 64 (narrower heads are zero-padded).
+    FDX_ATTN_PAD64=1 stores every head 64 wide (one head per 128-byte swizzle row)."""
+    if os.environ.get("FDX_ATTN_PAD64"):
+        return 64
+    return 32 if d <= 32 else 64
+
+
 class _SideStream:
     """Weight-gradient kernels have no consumer before the optimizer step, so the backward pass issues them
     on a second stream: the HBM-bound GroupNorm-backward kernels of the main (data-gradient) chain then
@@ -367,6 +375,27 @@ class Unet:
             temb, self._fourier_freqs(dev), W[tp + "0/kernel"], W[tp + "0/bias"], W[tp + "1/kernel"],
             W[tp + "1/bias"])
 
+        # Every ResidualBlock's timestep projection Dense(temb) (common.py:300-305) depends only on the embedding:
+        # all of them are issued NOW on a side stream (23 tiny GEMMs that each occupy a handful of SMs for
+        # 10-30 us), off the critical path; each block waits for its own row's event before its conv1.
+        rows: Dict[str, tuple] = {}
+        if not os.environ.get("FDX_NO_SIDE"):
+            side = self.__dict__.setdefault("_temb_stream", {}).get(str(dev))
+            if side is None:
+                side = self._temb_stream[str(dev)] = torch.cuda.Stream(device=dev)
+            ev0 = torch.cuda.Event()
+            ev0.record(torch.cuda.current_stream())
+            side.wait_event(ev0)
+            with torch.cuda.stream(side):
+                for kind, name, cin, cout in plan:
+                    if kind == "res":
+                        r = ops.linear_fwd(emb16, W16[f"{name}/temb_projection/kernel"],
+                                           bias=W[f"{name}/temb_projection/bias"], out_dtype=F32)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        rows[name] = (r, ev)
+        self._rows = rows
+
         # concat slot buffers: walk the plan once to find (x channels, skip channels, resolution)
         # skip k is produced by the k-th ("conv_in" | "push"); consumed by "cat" in LIFO order.
         res_of_skip, ch_of_skip = [], []
@@ -482,8 +511,14 @@ class Unet:
         cin, cout = x.shape[-1], dst.t.shape[-1]
         st1 = xin.stats(G)
         a1 = ops.groupnorm_apply(x, G, st1, W[f"{name}/{self._n1}/scale"], W[f"{name}/{self._n1}/bias"], eps, True)
-        row = ops.linear_fwd(emb16, W16[f"{name}/temb_projection/kernel"],
-                             bias=W[f"{name}/temb_projection/bias"], out_dtype=F32)
+        pre = self._rows.pop(name, None)
+        if pre is not None:                       # computed on the side stream at the start of the forward
+            row, ev = pre
+            torch.cuda.current_stream().wait_event(ev)
+            row.record_stream(torch.cuda.current_stream())
+        else:
+            row = ops.linear_fwd(emb16, W16[f"{name}/temb_projection/kernel"],
+                                 bias=W[f"{name}/temb_projection/bias"], out_dtype=F32)
         hnode = Node(torch.empty((x.shape[0], x.shape[1], x.shape[2], cout), dtype=BF16, device=x.device))
         hmid = ops.conv3x3_fwd(a1, W16[f"{name}/conv1/conv/kernel"], W[f"{name}/conv1/conv/bias"], rowvec=row,
                                out=hnode.t, colstats=hnode.colstats())
@@ -521,7 +556,7 @@ class Unet:
         Bn, hh, ww, C = x.shape
         L = hh * ww
         d = C // heads
-        dp = 32 if d <= 32 else 64
+        dp = _attn_width(d)
         if d > 64:
             raise FdxError(f"attention: head width {d} > 64 is not supported")
         HD = heads * dp
@@ -601,7 +636,7 @@ class Unet:
         Bn, L, C = xq.shape
         Lk, Cc = ctx.shape[1], ctx.shape[2]
         d = C // heads
-        dp = 32 if d <= 32 else 64
+        dp = _attn_width(d)
         if d > 64:
             raise FdxError(f"attention: head width {d} > 64 is not supported")
         HD = heads * dp
@@ -623,7 +658,7 @@ class Unet:
         Bn, L, C = xq.shape
         Lk, Cc = ctx.shape[1], ctx.shape[2]
         d = C // heads
-        dp = 32 if d <= 32 else 64
+        dp = _attn_width(d)
         HD = heads * dp
         M, Mk = Bn * L, Bn * Lk
         dev = xq.device
@@ -993,7 +1028,7 @@ class Unet:
         Bn, hh, ww, C = x.shape
         L = hh * ww
         d = C // heads
-        dp = 32 if d <= 32 else 64
+        dp = _attn_width(d)
         HD = heads * dp
         cross = ctx is not None
         kv_src = ctx if cross else xn.view(Bn, L, C)
