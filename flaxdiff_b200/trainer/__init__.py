@@ -501,7 +501,7 @@ class GeneralDiffusionTrainer:
         if self._overlap:
             self._gbuf[-64:-63].copy_(loss)
             self._exchange.begin()
-            self._exchange.finish([])
+            self._exchange.finish([torch.cuda.current_stream()])
             loss = self._gbuf[-64:-63]
         return loss
 
@@ -528,7 +528,7 @@ class GeneralDiffusionTrainer:
             self._gbuf[-64:-63].copy_(loss)
             self._exchange.begin()
             self.model.backward(st.params, saved, dF, grads, on_ready=self._exchange.ready)
-            self._exchange.finish([])
+            self._exchange.finish([torch.cuda.current_stream()])
             return self._gbuf[-64:-63]
         self.model.backward(st.params, saved, dF, grads)
         return loss
@@ -566,6 +566,8 @@ class GeneralDiffusionTrainer:
                 loss = self._graphed_fwd_bwd(images, noise, noise_level, ctx)
             else:
                 loss = self._fwd_bwd(images, noise, noise_level, ctx)
+                if self._overlap:
+                    loss = loss.clone()             # a view of the exchange buffer's tail otherwise
             gscale = 1.0
             if self.distributed_training and self.world_size > 1 and not self._overlap:
                 if self._exchange is not None:           # one un-overlapped call over gradients + loss tail
