@@ -310,11 +310,17 @@ def profile_kernels(trainer, images, noise, t, ctx=None):
         dy, dx = a[0], a[2]
         return conv_flops(dy.shape[0], dy.shape[1], dy.shape[2], dx.shape[3], dy.shape[3])
 
-    def f_attn(a, k):
-        return float(k.get("_flops", 0.0))
+    def f_attn_fwd(a, k):    # q, k, v, heads, dh, scale: QK^T + PV at the TRUE head width (1 / scale^2)
+        q, kk, heads, scale = a[0], a[1], a[3], a[5]
+        return 4.0 * q.shape[0] * heads * q.shape[1] * kk.shape[1] * round(scale ** -2)
+
+    def f_attn_bwd(a, k):    # q, k, v, o, lse, d_o, heads, dh, scale: dV, dP, dQ, dK
+        q, kk, heads, scale = a[0], a[1], a[6], a[8]
+        return 8.0 * q.shape[0] * heads * q.shape[1] * kk.shape[1] * round(scale ** -2)
 
     table = {"conv3x3_fwd": f_fwd, "conv3x3_dgrad": f_dgrad, "conv3x3_wgrad": f_wgrad, "gemm": f_gemm,
-             "upconv3x3_fwd": f_up_fwd, "upconv3x3_dgrad": f_up_dgrad, "upconv3x3_wgrad": f_wgrad}
+             "upconv3x3_fwd": f_up_fwd, "upconv3x3_dgrad": f_up_dgrad, "upconv3x3_wgrad": f_wgrad,
+             "attention_fwd": f_attn_fwd, "attention_bwd": f_attn_bwd}
     orig = {n: getattr(ops, n) for n in table}
     recs = []
 
