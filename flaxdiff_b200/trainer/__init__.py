@@ -595,10 +595,9 @@ class GeneralDiffusionTrainer:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
-            # NCCL launches inside the capture: other threads (NCCL's proxy, the prefetcher) must stay free to
-            # call the CUDA API -> thread-local capture mode
-            mode = "thread_local" if self._overlap else "global"
-            with torch.cuda.graph(self._graph, capture_error_mode=mode):
+            # other threads must stay free to call the CUDA API during the capture (NCCL's proxy thread for the
+            # captured all-reduce launches, the DevicePrefetcher's pin_memory / copies) -> thread-local mode
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
                 self._static_loss = self._fwd_bwd(*self._static)
         self._static[0].copy_(images, non_blocking=True)
         self._static[1].copy_(noise)
