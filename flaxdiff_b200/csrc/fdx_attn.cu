@@ -73,17 +73,24 @@ __device__ __forceinline__ void store_p_chunk(uint32_t sP, int r, int c0, const 
 // ======================================================================================================
 // forward
 // ======================================================================================================
-template <int DH>
-__global__ void __launch_bounds__(kThreads, 1)
+// SHORT = the keys fit one 128-key block (77 text tokens): no ring, one P tile, 256 TMEM columns and 80 KB of
+// shared memory, so TWO CTAs share an SM - with L/128 x heads x B short-lived CTAs (131 072 at 128x128, B = 128)
+// the prologue (barrier init, TMEM allocation, first TMA round trip) of one overlaps the math of the other.
+template <int DH, bool SHORT>
+__global__ void __launch_bounds__(kThreads, SHORT ? 2 : 1)
 fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                     const __grid_constant__ CUtensorMap mapV, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  constexpr int NKV = SHORT ? 1 : kKV;               // K/V ring stages
+  constexpr int NPB = SHORT ? 1 : 2;                 // P tiles
+  constexpr uint32_t O_COL = SHORT ? 128u : 256u;    // first TMEM column of the O accumulator(s)
+  constexpr uint32_t TMEM_COLS = SHORT ? 256u : 512u;
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + kTile;                       // kKV x (K tile, V tile)
-  uint8_t* sP = sKV + kKV * 2 * kTile;               // 2 x (two 64-key chunks)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * 2 * kTile);
+  uint8_t* sKV = smem + kTile;                       // NKV x (K tile, V tile)
+  uint8_t* sP = sKV + NKV * 2 * kTile;               // NPB x (two 64-key chunks)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NPB * 2 * kTile);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;          // [kKV]
   uint64_t* kv_empty = bars + 1 + kKV;   // [kKV]
@@ -106,7 +113,7 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -117,8 +124,8 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       mbar_arrive_expect_tx(q_full, kTile);
       tma_load_4d(sQ, &mapQ, q_full, c0, q0, b, 0);
       for (int j = 0; j < nblk; ++j) {
-        const int s = j % kKV;
-        mbar_wait(&kv_empty[s], ((j / kKV) & 1) ^ 1);
+        const int s = j % NKV;
+        mbar_wait(&kv_empty[s], ((j / NKV) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], 2 * kTile);
         tma_load_4d(sKV + s * 2 * kTile, &mapK, &kv_full[s], c0, j * 128, b, 0);
         tma_load_4d(sKV + s * 2 * kTile + kTile, &mapV, &kv_full[s], c0, j * 128, b, 0);
@@ -130,8 +137,8 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       constexpr uint32_t idO = umma_idesc_bf16(128, DH, 0, 1);
       const uint32_t aQ = smem_u32(sQ) + koff;
       auto issue_s = [&](int j) {
-        const int s = j % kKV;
-        mbar_wait(&kv_full[s], (j / kKV) & 1);
+        const int s = j % NKV;
+        mbar_wait(&kv_full[s], (j / NKV) & 1);
         tc_fence_after();
         const uint32_t aK = smem_u32(sKV + s * 2 * kTile) + koff;
 #pragma unroll
@@ -147,12 +154,12 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         if (j + 1 < nblk) issue_s(j + 1);
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        const int s = j % kKV;
-        const uint32_t aP = smem_u32(sP + (j & 1) * 2 * kTile);
+        const int s = j % NKV;
+        const uint32_t aP = smem_u32(sP + (j % NPB) * 2 * kTile);
         const uint32_t aV = smem_u32(sKV + s * 2 * kTile + kTile) + koff;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_f16(tmem_base + 256u + (uint32_t)((j & 1) * 64),
+          umma_f16(tmem_base + O_COL + (uint32_t)((j & 1) * 64),
                    umma_desc_sw128(aP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
                    umma_desc_sw128(aV + k * 2048, 8192, 1024), idO, k != 0 ? 1u : 0u);
         umma_commit(&o_full[j & 1]);
@@ -174,7 +181,7 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 #pragma unroll
       for (int c = 0; c < DH; c += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(lane_addr + 256u + (uint32_t)((j & 1) * 64 + c), v);
+        tmem_ld_32x32(lane_addr + O_COL + (uint32_t)((j & 1) * 64 + c), v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], corr, __uint_as_float(v[i]));
@@ -201,7 +208,7 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       const float corr = ex2(m - m_new);           // first block: exp2(-inf) = 0
       // pass B: probabilities -> bf16 -> the swizzled A tile of the PV MMA
       float rs = 0.f;
-      const uint32_t sPj = smem_u32(sP + (j & 1) * 2 * kTile);
+      const uint32_t sPj = smem_u32(sP + (j % NPB) * 2 * kTile);
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         uint32_t v[32], w[16];
@@ -243,7 +250,7 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ======================================================================================================
@@ -525,22 +532,25 @@ int fdx_attention_fwd(const fdx_attn_desc* a, void* stream) {
   d.scale = a->scale; d.scale_log2 = a->scale * kLog2e;
   d.o = (__nv_bfloat16*)a->o; d.o_ld = a->o_ld; d.o_bs = a->o_bs;
   d.lse = a->lse;
-  const int smem = (1 + 2 * kKV + 4) * kTile + 1024 + 256;
+  const bool short_keys = a->Lk <= 128;
+  const int smem = (short_keys ? (1 + 2 + 2) : (1 + 2 * kKV + 4)) * kTile + 1024 + 256;
   dim3 grid((a->L + 127) / 128, a->heads, a->B);
-  static bool attr[2] = {false, false};
-  if (a->dh == 64) {
-    if (!attr[0]) {
-      FDX_CUDA(cudaFuncSetAttribute(fdx_attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr[0] = true;
-    }
-    fdx_attn_fwd_kernel<64><<<grid, kThreads, smem, (cudaStream_t)stream>>>(mQ, mK, mV, d);
-  } else {
-    if (!attr[1]) {
-      FDX_CUDA(cudaFuncSetAttribute(fdx_attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr[1] = true;
-    }
-    fdx_attn_fwd_kernel<32><<<grid, kThreads, smem, (cudaStream_t)stream>>>(mQ, mK, mV, d);
+  static bool attr[4] = {false, false, false, false};
+#define FDX_ATTN_FWD_LAUNCH(DHV, SH, IDX)                                                                      \
+  {                                                                                                            \
+    if (!attr[IDX]) {                                                                                          \
+      FDX_CUDA(cudaFuncSetAttribute(fdx_attn_fwd_kernel<DHV, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                    smem));                                                                    \
+      attr[IDX] = true;                                                                                        \
+    }                                                                                                          \
+    fdx_attn_fwd_kernel<DHV, SH><<<grid, kThreads, smem, (cudaStream_t)stream>>>(mQ, mK, mV, d);                \
   }
+  if (a->dh == 64) {
+    if (short_keys) FDX_ATTN_FWD_LAUNCH(64, true, 0) else FDX_ATTN_FWD_LAUNCH(64, false, 1)
+  } else {
+    if (short_keys) FDX_ATTN_FWD_LAUNCH(32, true, 2) else FDX_ATTN_FWD_LAUNCH(32, false, 3)
+  }
+#undef FDX_ATTN_FWD_LAUNCH
   fdx_note_kernel(FDX_KERNEL_ATTN_FWD);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
