@@ -1,0 +1,22 @@
+"""Which kernel generation runs by default.  Every round-2 kernel has its round-1 predecessor one environment
+switch away (DESIGN.md $6); this module turns a False below into that switch at import time, BEFORE libfdx is
+loaded, so that reverting a kernel that misbehaves on some box is a one-word change and never a code edit in
+the hot path.  An explicit environment variable always wins."""
+import os
+
+ROUND2_DEFAULTS = {
+    # name: (enabled, environment variable that selects the predecessor)
+    "fused_attention": (True, "FDX_ATTN_UNFUSED"),     # fdx_attention_fwd/bwd vs separate QK^T / softmax / PV launches
+    "wgrad9k": (True, "FDX_WGRAD9_V1"),                # ky-pairs-in-M weight gradient vs the round-1 nine-tap kernels
+    "gn_cluster_bwd": (True, "FDX_GN_2PASS"),          # one-launch cluster GroupNorm backward vs the two-pass one
+    "dp_overlap": (True, "FDX_NO_DP_OVERLAP"),         # bucketed all-reduce inside the training graph vs one call after it
+}
+
+
+def apply() -> None:
+    for _name, (enabled, env) in ROUND2_DEFAULTS.items():
+        if not enabled and env not in os.environ:
+            os.environ[env] = "1"
+
+
+apply()
