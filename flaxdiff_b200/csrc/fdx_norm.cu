@@ -654,6 +654,272 @@ gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
   }
 }
 
+// ---- GroupNorm(+SiLU) backward as ONE persistent, software-pipelined launch (any image size) ------------
+// The cluster kernel above needs a whole image's x + dy (times the images in flight) inside the L2; a
+// 256x256x64 image alone is 16.8 MB.  Here the batch is cut into STAGES of whole images sized so that two
+// stages fit the L2 (~24 MB each).  A grid of co-resident CTAs (cooperative launch) walks the stages in
+// lock step: pass 1 of stage s (per-channel sums -> global atomics, then one release-increment of the
+// stage's arrival counter), then - after an acquire-spin on stage s-1's counter, which every CTA reaches at
+// about the same time - pass 2 of stage s-1 from L2.  One launch, x and dy read from HBM once.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool SILU, bool ACC, bool CS>
+__global__ void __launch_bounds__(kNT, 2)
+gn_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ x, long long xps, const __nv_bfloat16* __restrict__ dy,
+                   long long dps, int N, int HW, int C, int G, int imgs_per_stage,
+                   const float* __restrict__ stats, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float eps, float* __restrict__ ws,
+                   unsigned* __restrict__ counters, __nv_bfloat16* __restrict__ dx, long long dxps,
+                   float* __restrict__ csum_img) {
+  const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
+  const int tid = threadIdx.x;
+  extern __shared__ float shm[];
+  float* part0 = shm;                      // [rows*C]
+  float* part1 = part0 + rows * C;         // [rows*C]
+  float* redg = part1 + rows * C;          // [2*G]
+  const float cnt = (float)HW * (float)cpg;
+  const bool active = tid < rows * vpp;
+  const int cv = tid % vpp, r = tid / vpp;
+  const int g = (cv * 8) / cpg;
+  const int nstage = (N + imgs_per_stage - 1) / imgs_per_stage;
+  const unsigned nctas = gridDim.x;
+  float gam[8], bet[8];
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gam[j] = gamma[cv * 8 + j]; bet[j] = beta[cv * 8 + j]; }
+  }
+
+  // this CTA's pixel slice [lo, hi) of stage s, in the stage's flattened (image, pixel) space
+  auto slice = [&](int s, long long& lo, long long& hi, int& n0) {
+    n0 = s * imgs_per_stage;
+    const int n1 = min(N, n0 + imgs_per_stage);
+    const long long total = (long long)(n1 - n0) * HW;
+    long long per = (total + nctas - 1) / nctas;
+    per = (per + rows - 1) / rows * rows;
+    lo = min(total, (long long)blockIdx.x * per);
+    hi = min(total, lo + per);
+  };
+  auto coeffs = [&](int n, float& mean, float& rstd, GnPair4& ah, GnPair4& bh) {
+    mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
+    const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+    rstd = rsqrtf(var + eps);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a0 = rstd * gam[2 * j], a1 = rstd * gam[2 * j + 1];
+      ah.v[j] = f2_pack(0.5f * a0, 0.5f * a1);
+      bh.v[j] = SILU ? f2_pack(0.5f * (bet[2 * j] - mean * a0), 0.5f * (bet[2 * j + 1] - mean * a1)) : f2_pack(0.f, 0.f);
+    }
+  };
+
+  auto pass1 = [&](int s) {
+    long long lo, hi; int n0;
+    slice(s, lo, hi, n0);
+    for (long long seg = lo; seg < hi;) {
+      const int img = (int)(seg / HW);
+      const long long seg_hi = min(hi, (long long)(img + 1) * HW);
+      const int n = n0 + img;
+      if (active) {
+        float mean, rstd; GnPair4 ah, bh, s0, s1;
+        coeffs(n, mean, rstd, ah, bh);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s0.v[j] = f2_pack(0.f, 0.f); s1.v[j] = f2_pack(0.f, 0.f); }
+        const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
+        const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
+        const int p_lo = (int)(seg - (long long)img * HW), p_hi = (int)(seg_hi - (long long)img * HW);
+        for (int p0 = p_lo + r; p0 < p_hi; p0 += kBU * rows) {
+          uint4 xu[kBU], du[kBU];
+#pragma unroll
+          for (int k = 0; k < kBU; ++k) {
+            const int p = p0 + k * rows;
+            xu[k] = make_uint4(0, 0, 0, 0);
+            du[k] = make_uint4(0, 0, 0, 0);
+            if (p < p_hi) {
+              xu[k] = *reinterpret_cast<const uint4*>(xb + (long long)p * xps);
+              du[k] = *reinterpret_cast<const uint4*>(db_ + (long long)p * dps);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kBU; ++k) {
+            const uint32_t xw[4] = {xu[k].x, xu[k].y, xu[k].z, xu[k].w};
+            const uint32_t dw[4] = {du[k].x, du[k].y, du[k].z, du[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const f32x2_t xv = f2_from_bf16x2(xw[j]);
+              const f32x2_t dz = gn_dz_pair<SILU, false>(xv, f2_from_bf16x2(dw[j]), ah.v[j], bh.v[j]);
+              s0.v[j] = f2_add(s0.v[j], dz);
+              s1.v[j] = f2_fma(dz, xv, s1.v[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float l0, h0;
+          f2_unpack(s0.v[j], l0, h0);
+          part0[r * C + cv * 8 + 2 * j] = l0; part0[r * C + cv * 8 + 2 * j + 1] = h0;
+          f2_unpack(s1.v[j], l0, h0);
+          part1[r * C + cv * 8 + 2 * j] = l0; part1[r * C + cv * 8 + 2 * j + 1] = h0;
+        }
+      }
+      __syncthreads();
+      for (int c = tid; c < C; c += kNT) {
+        float t0 = 0.f, t1 = 0.f;
+        for (int rr = 0; rr < rows; ++rr) { t0 += part0[rr * C + c]; t1 += part1[rr * C + c]; }
+        atomicAdd(&ws[((long long)n * C + c) * 2], t0);
+        atomicAdd(&ws[((long long)n * C + c) * 2 + 1], t1);
+      }
+      __syncthreads();
+      seg = seg_hi;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(&counters[s], 1u);
+  };
+
+  auto pass2 = [&](int s) {
+    if (tid == 0) {
+      while (ld_acquire_u32(&counters[s]) < nctas) __nanosleep(100);
+    }
+    __syncthreads();
+    long long lo, hi; int n0;
+    slice(s, lo, hi, n0);
+    for (long long seg = lo; seg < hi;) {
+      const int img = (int)(seg / HW);
+      const long long seg_hi = min(hi, (long long)(img + 1) * HW);
+      const int n = n0 + img;
+      if (tid < 2 * G) redg[tid] = 0.f;
+      __syncthreads();
+      for (int c = tid; c < C; c += kNT) {
+        const float S0 = __ldcg(&ws[((long long)n * C + c) * 2]), S1 = __ldcg(&ws[((long long)n * C + c) * 2 + 1]);
+        const int gc = c / cpg;
+        const float mg = stats[(long long)n * 2 * G + 2 * gc] / cnt;
+        const float vg = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * gc + 1] / cnt - mg * mg);
+        const float rg = rsqrtf(vg + eps), ga = gamma[c];
+        atomicAdd(&redg[2 * gc], ga * S0);
+        atomicAdd(&redg[2 * gc + 1], ga * rg * (S1 - mg * S0));
+      }
+      __syncthreads();
+      if (active) {
+        float mean, rstd; GnPair4 ah, bh, cs;
+        coeffs(n, mean, rstd, ah, bh);
+        const float m1 = redg[2 * g] / cnt, m2 = redg[2 * g + 1] / cnt;
+        const float c2 = rstd * rstd * m2;
+        const float c3 = mean * c2 - rstd * m1;
+        const f32x2_t nc2 = f2_pack(-c2, -c2), c3p = f2_pack(c3, c3);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cs.v[j] = f2_pack(0.f, 0.f);
+        const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
+        const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
+        __nv_bfloat16* ob = dx + (long long)n * HW * dxps + cv * 8;
+        const int p_lo = (int)(seg - (long long)img * HW), p_hi = (int)(seg_hi - (long long)img * HW);
+        for (int p0 = p_lo + r; p0 < p_hi; p0 += kBU * rows) {
+          uint4 xu[kBU], du[kBU], ou[kBU];
+#pragma unroll
+          for (int k = 0; k < kBU; ++k) {
+            const int p = p0 + k * rows;
+            xu[k] = make_uint4(0, 0, 0, 0);
+            du[k] = make_uint4(0, 0, 0, 0);
+            ou[k] = make_uint4(0, 0, 0, 0);
+            if (p < p_hi) {
+              xu[k] = *reinterpret_cast<const uint4*>(xb + (long long)p * xps);
+              du[k] = *reinterpret_cast<const uint4*>(db_ + (long long)p * dps);
+              if (ACC) ou[k] = *reinterpret_cast<const uint4*>(ob + (long long)p * dxps);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kBU; ++k) {
+            const int p = p0 + k * rows;
+            if (p < p_hi) {
+              const uint32_t xw[4] = {xu[k].x, xu[k].y, xu[k].z, xu[k].w};
+              const uint32_t dw[4] = {du[k].x, du[k].y, du[k].z, du[k].w};
+              const uint32_t ow[4] = {ou[k].x, ou[k].y, ou[k].z, ou[k].w};
+              uint32_t res[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const f32x2_t xv = f2_from_bf16x2(xw[j]);
+                const f32x2_t dz2 = gn_dz_pair<SILU, true>(xv, f2_from_bf16x2(dw[j]), ah.v[j], bh.v[j]);
+                f32x2_t v = f2_fma(dz2, ah.v[j], f2_fma(xv, nc2, c3p));
+                if (CS) cs.v[j] = f2_add(cs.v[j], v);
+                if (ACC) v = f2_add(v, f2_from_bf16x2(ow[j]));
+                res[j] = f2_to_bf16x2(v);
+              }
+              *reinterpret_cast<uint4*>(ob + (long long)p * dxps) = make_uint4(res[0], res[1], res[2], res[3]);
+            }
+          }
+        }
+        if (CS) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float l0, h0;
+            f2_unpack(cs.v[j], l0, h0);
+            part0[r * C + cv * 8 + 2 * j] = l0;
+            part0[r * C + cv * 8 + 2 * j + 1] = h0;
+          }
+        }
+      }
+      if (CS) {
+        __syncthreads();
+        for (int c = tid; c < C; c += kNT) {
+          float v = 0.f;
+          for (int rr = 0; rr < rows; ++rr) v += part0[rr * C + c];
+          atomicAdd(&csum_img[(long long)n * C + c], v);
+        }
+      }
+      __syncthreads();
+      seg = seg_hi;
+    }
+  };
+
+  for (int s = 0; s < nstage; ++s) {
+    pass1(s);
+    if (s > 0) pass2(s - 1);
+  }
+  pass2(nstage - 1);
+}
+
+template <bool SILU, bool ACC, bool CS>
+int launch_bwd_pipe(const fdx_act* x, const fdx_act* dy, int groups, const float* stats, const float* gamma,
+                    const float* beta, float eps, float* ws, unsigned* counters, int max_stages,
+                    const fdx_act* dx, float* csum_img, cudaStream_t st) {
+  const int C = x->c, HW = x->h * x->w, N = x->n;
+  const size_t shm = sizeof(float) * (2 * (size_t)(kNT / (C / 8)) * C + 2 * groups);
+  static int occ = 0;
+  if (occ == 0) {
+    FDX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_bwd_pipe_kernel<SILU, ACC, CS>, kNT, 20 * 1024));
+    if (occ > 2) occ = 2;
+    if (occ < 1) occ = 1;
+  }
+  const int sms = fdx_num_sms();
+  const int grid = sms * occ;
+  // stage = whole images, ~24 MB of x + dy (two stages in flight), at least one image
+  const double img_bytes = 4.0 * HW * C;
+  int ips = (int)(24.0 * 1024 * 1024 / img_bytes);
+  if (ips < 1) ips = 1;
+  if (ips > N) ips = N;
+  while ((N + ips - 1) / ips > max_stages) ++ips;
+  const int nstage = (N + ips - 1) / ips;
+  FDX_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned) * nstage, st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kNT);
+  cfg.dynamicSmemBytes = shm;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident: the stage counters are spin-waited
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FDX_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_pipe_kernel<SILU, ACC, CS>, (const __nv_bfloat16*)x->ptr,
+                              (long long)x->pix_stride, (const __nv_bfloat16*)dy->ptr, (long long)dy->pix_stride, N,
+                              HW, C, groups, ips, stats, gamma, beta, eps, ws, counters, (__nv_bfloat16*)dx->ptr,
+                              (long long)dx->pix_stride, csum_img));
+  fdx_count_launch();
+  return FDX_OK;
+}
+
 template <bool SILU, bool ACC, bool CS>
 int launch_bwd_cluster(int CL, size_t shm, const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
                        const float* gamma, const float* beta, float eps, float* ws, const fdx_act* dx,
@@ -912,6 +1178,39 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
   while (CL > 1 && (HW / CL) < 4 * (kNT / (C / 8))) CL >>= 1;  // keep >= 4 row iterations per CTA
   // images in flight with one CTA per SM = 148 / CL; beyond ~64 MB the second pass would miss in L2 anyway
   const bool fits_l2 = (148.0 / CL) * img_bytes <= 64.0 * 1024 * 1024;
+  // FDX_GN_PIPE=1: the persistent pipelined kernel for the shapes the cluster path cannot take (large images);
+  // FDX_GN_PIPE=2: for every shape.  Its stage counters live behind `red` in the caller's workspace
+  // (2*N*groups floats >= the <= 2*N stages ever needed... capped to that many stages).
+  static const int pipe = getenv("FDX_GN_PIPE") ? atoi(getenv("FDX_GN_PIPE")) : 0;
+  if (!two_pass && pipe > 0 && (pipe > 1 || !(HW >= 1024 && fits_l2)) && (long long)N * HW >= 4096) {
+    FDX_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, st));
+    if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * N * C, st));
+    unsigned* counters = reinterpret_cast<unsigned*>(red);
+    const int max_stages = 2 * N * groups;
+    const int key = (silu ? 4 : 0) | (accumulate ? 2 : 0) | (csum_img ? 1 : 0);
+    int rc;
+#define FDX_GN_PP(S, A, CSF) rc = launch_bwd_pipe<S, A, CSF>(x, dy, groups, stats, gamma, beta, eps, sums, counters, max_stages, dx, csum_img, st)
+    switch (key) {
+      case 0: FDX_GN_PP(false, false, false); break;
+      case 1: FDX_GN_PP(false, false, true); break;
+      case 2: FDX_GN_PP(false, true, false); break;
+      case 3: FDX_GN_PP(false, true, true); break;
+      case 4: FDX_GN_PP(true, false, false); break;
+      case 5: FDX_GN_PP(true, false, true); break;
+      case 6: FDX_GN_PP(true, true, false); break;
+      default: FDX_GN_PP(true, true, true); break;
+    }
+#undef FDX_GN_PP
+    if (rc != FDX_OK) return rc;
+    const int cb = (C + kFinC - 1) / kFinC;
+    gn_bwd_finalize_kernel<<<cb, 256, 0, st>>>(sums, stats, gamma, N, HW, C, groups, eps, cb, red, dgamma, dbeta);
+    FDX_LAUNCH_CHECK();
+    if (csum_tot) {
+      reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(csum_img, N, C, csum_tot, 0);
+      FDX_LAUNCH_CHECK();
+    }
+    return FDX_OK;
+  }
   if (!two_pass && HW >= 1024 && fits_l2) {
     // CTAs per SM so that (148 * per_sm / CL) images * img_bytes <= 48 MB, at least 1
     int per_sm = (int)((48.0 * 1024 * 1024 * CL) / (148.0 * img_bytes));

@@ -6,5 +6,8 @@ timeout 300 python tests/gpu_bench_layers.py 64 256 wgrad > gpurun_out/layers_r0
 FDX_WGRAD9_V1=1 timeout 300 python tests/gpu_bench_layers.py 64 256 wgrad > gpurun_out/layers_r02_64_wgrad9_v1.txt 2>&1
 timeout 300 python tests/gpu_bench_layers.py 64 256 gnonly > gpurun_out/layers_r02_gn_cluster.txt 2>&1
 FDX_GN_2PASS=1 timeout 300 python tests/gpu_bench_layers.py 64 256 gnonly > gpurun_out/layers_r02_gn_2pass.txt 2>&1
+FDX_GN_PIPE=2 timeout 300 python tests/gpu_bench_layers.py 64 256 gnonly > gpurun_out/layers_r02_gn_pipe.txt 2>&1
+timeout 300 python tests/gpu_bench_layers.py 256 64 gnonly > gpurun_out/layers_r02_gn256_default.txt 2>&1
+FDX_GN_PIPE=1 timeout 300 python tests/gpu_bench_layers.py 256 64 gnonly > gpurun_out/layers_r02_gn256_pipe.txt 2>&1
 timeout 300 python tests/gpu_bench_attention.py > gpurun_out/layers_r02_attention.txt 2>&1
-tail -3 gpurun_out/layers_r02_64_wgrad9k.txt gpurun_out/layers_r02_64_wgrad9_v1.txt; tail -2 gpurun_out/layers_r02_gn_cluster.txt gpurun_out/layers_r02_gn_2pass.txt; cat gpurun_out/layers_r02_attention.txt
+tail -3 gpurun_out/layers_r02_64_wgrad9k.txt gpurun_out/layers_r02_64_wgrad9_v1.txt; tail -2 gpurun_out/layers_r02_gn_cluster.txt gpurun_out/layers_r02_gn_2pass.txt gpurun_out/layers_r02_gn_pipe.txt gpurun_out/layers_r02_gn256_default.txt gpurun_out/layers_r02_gn256_pipe.txt; cat gpurun_out/layers_r02_attention.txt
