@@ -25,6 +25,7 @@
 #include "fdx_common.cuh"
 #include "../../include/fdx.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -532,7 +533,7 @@ int fdx_attention_fwd(const fdx_attn_desc* a, void* stream) {
   d.scale = a->scale; d.scale_log2 = a->scale * kLog2e;
   d.o = (__nv_bfloat16*)a->o; d.o_ld = a->o_ld; d.o_bs = a->o_bs;
   d.lse = a->lse;
-  const bool short_keys = a->Lk <= 128;
+  const bool short_keys = a->Lk <= 128 && !getenv("FDX_ATTN_NO_SHORT");
   const int smem = (short_keys ? (1 + 2 + 2) : (1 + 2 * kKV + 4)) * kTile + 1024 + 256;
   dim3 grid((a->L + 127) / 128, a->heads, a->B);
   static bool attr[4] = {false, false, false, false};

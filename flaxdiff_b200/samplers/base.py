@@ -53,7 +53,8 @@ class _GraphedEval:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread-local capture mode: a data-loading / prefetch thread may call the CUDA API meanwhile
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.static_out = fn(*self.static_in)
 
     def __call__(self, *inputs, clone: bool = True):

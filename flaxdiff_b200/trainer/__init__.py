@@ -322,39 +322,70 @@ class TrainState:
 # --------------------------------------------------------------------------- host -> device prefetch
 class DevicePrefetcher:
     """uint8 host -> device prefetch (the reference's daemon prefetch thread, data/dataloaders.py:28-82, plus
-    jax.device_put): a background thread pulls batches from the iterator, stages the sample tensor in a
-    pinned buffer and copies it to the device on a copy stream, `depth` batches ahead of the consumer.
-    Yields batches whose sample entry is a device tensor the consumer may use on its current stream."""
+    jax.device_put): a background thread pulls batches from the iterator, stages the sample tensor in one of a
+    small RING of pinned buffers (allocated once, in the constructor's thread: no cudaHostAlloc ever runs
+    concurrently with a CUDA-graph capture) and copies it to the device on a copy stream, `depth` batches ahead
+    of the consumer.  Yields batches whose sample entry is a device tensor usable on the current stream."""
 
     def __init__(self, it, key: str, device, depth: int = 2):
-        self.it, self.key, self.device = iter(it), key, torch.device(device)
-        self.q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
+        self.it, self.key = iter(it), key
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.depth = max(1, depth)
+        self.q: "queue.Queue" = queue.Queue(maxsize=self.depth)
         self.stream = torch.cuda.Stream(device=self.device)
         self._stop = False
-        self.th = threading.Thread(target=self._run, daemon=True)
+        self._ring: List[torch.Tensor] = []
+        self._free: "queue.Queue" = queue.Queue()
+        # the first batch is staged here, synchronously: it sizes the pinned ring
+        try:
+            first = next(self.it)
+        except StopIteration:
+            first = None
+        if first is not None:
+            data = self._as_tensor(first[self.key])
+            for _ in range(self.depth + 2):
+                buf = torch.empty(tuple(data.shape), dtype=data.dtype).pin_memory()
+                self._ring.append(buf)
+                self._free.put(buf)
+            self.q.put(self._stage(first, data))
+        self.th = threading.Thread(target=self._run, args=(first is None,), daemon=True)
         self.th.start()
 
-    def _run(self):
-        torch.cuda.set_device(self.device)
+    @staticmethod
+    def _as_tensor(data):
+        if not isinstance(data, torch.Tensor):
+            data = torch.as_tensor(np.asarray(data))
+        if data.dtype not in (torch.uint8, torch.float32):
+            data = data.to(torch.float32)
+        return data
+
+    def _stage(self, batch, data):
+        if self._ring and tuple(data.shape) == tuple(self._ring[0].shape) and data.dtype == self._ring[0].dtype:
+            pinned = self._free.get()
+            pinned.copy_(data)
+        else:                                   # ragged last batch: one-off pinned copy
+            pinned = data.contiguous().pin_memory()
+        with torch.cuda.stream(self.stream):
+            dev = pinned.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        out = dict(batch)
+        out[self.key] = dev
+        return (out, ev, pinned)
+
+    def _run(self, empty: bool):
         try:
-            for batch in self.it:
-                if self._stop:
-                    break
-                data = batch[self.key]
-                if not isinstance(data, torch.Tensor):
-                    data = torch.as_tensor(np.asarray(data))
-                if data.dtype not in (torch.uint8, torch.float32):
-                    data = data.to(torch.float32)
-                pinned = data if data.is_pinned() else data.contiguous().pin_memory()
-                with torch.cuda.stream(self.stream):
-                    dev = pinned.to(self.device, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(self.stream)
-                out = dict(batch)
-                out[self.key] = dev
-                self.q.put((out, ev, pinned))
+            torch.cuda.set_device(self.device)
+            if not empty:
+                for batch in self.it:
+                    if self._stop:
+                        break
+                    self.q.put(self._stage(batch, self._as_tensor(batch[self.key])))
             self.q.put(None)
-        except Exception as e:  # noqa: BLE001 - surfaced to the consumer
+        except BaseException as e:  # noqa: BLE001 - surfaced to the consumer
             self.q.put(e)
 
     def __iter__(self):
@@ -364,15 +395,25 @@ class DevicePrefetcher:
         item = self.q.get()
         if item is None:
             raise StopIteration
-        if isinstance(item, Exception):
+        if isinstance(item, BaseException):
             raise item
-        batch, ev, _pinned = item
+        batch, ev, pinned = item
         torch.cuda.current_stream().wait_event(ev)
         batch[self.key].record_stream(torch.cuda.current_stream())
+        if any(pinned is b for b in self._ring):
+            ev.synchronize()                    # the H2D copy has left the pinned buffer: recycle it
+            self._free.put(pinned)
         return batch
 
     def close(self):
         self._stop = True
+        try:                                    # unblock a producer waiting on a full queue / an empty ring
+            while True:
+                self.q.get_nowait()
+        except queue.Empty:
+            pass
+        for b in self._ring:
+            self._free.put(b)
 
 
 # --------------------------------------------------------------------------- trainer
@@ -691,15 +732,16 @@ class GeneralDiffusionTrainer:
         then per epoch train -> validation sampling from the EMA weights -> best-state tracking
         (-> orbax-layout checkpoint when `save_checkpoints`)."""
         steps_pe = training_steps_per_epoch if training_steps_per_epoch is not None else train_steps_per_epoch
-        train_ds = iter(data['train']())
-        if prefetch and self.device.type == "cuda":
-            train_ds = DevicePrefetcher(train_ds, self.input_config.sample_data_key, self.device, prefetch)
         val_ds = data.get('val', data.get('test', None))
         step_fn = self._define_train_step(data.get('local_batch_size'))
         val_step = self._define_validation_step(sampler_class, sampling_noise_schedule)
         if val_steps_per_epoch > 0:
+            # sanity validation first (it also captures the sampler's graphs before any background thread exists)
             self.validation_loop(self.state, val_step, val_ds, val_steps_per_epoch, self.latest_step,
                                  val_diffusion_steps)
+        train_ds = iter(data['train']())
+        if prefetch and self.device.type == "cuda":
+            train_ds = DevicePrefetcher(train_ds, self.input_config.sample_data_key, self.device, prefetch)
         while self.latest_step < epochs * steps_pe:
             epoch = self.latest_step // steps_pe
             t0 = time.time()

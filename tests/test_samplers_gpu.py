@@ -10,7 +10,7 @@ from flaxdiff_b200.inputs import DiffusionInputConfig
 from flaxdiff_b200.models.simple_unet import Unet
 from flaxdiff_b200.predictors import EpsilonPredictionTransform, KarrasPredictionTransform
 from flaxdiff_b200.samplers import MultiStepDPM, RK4Sampler, SimpleDDPMSampler, SimplifiedEulerSampler
-from flaxdiff_b200.schedulers import CosineNoiseScheduler, KarrasVENoiseScheduler
+from flaxdiff_b200.schedulers import KarrasVENoiseScheduler, LinearNoiseSchedule
 from oracle import diffusion_ref as R
 from oracle import train_ref, unet_ref
 
@@ -72,19 +72,21 @@ def test_karras_family_samplers_vs_oracle(kind, graph):
 
 
 def test_simple_ddpm_sampler_vs_oracle(monkeypatch):
-    """SimpleDDPMSampler on a variance-preserving continuous schedule (cosine), epsilon prediction."""
+    """SimpleDDPMSampler on the variance-preserving LinearNoiseSchedule(1000), epsilon prediction, from step 700
+    (sqrt(alpha_bar) = 0.085 there; at step 999 it is 0.006 and x0 = (x - sigma eps) / alpha amplifies the bf16
+    noise of the first evaluation 150-fold, which tests conditioning rather than the update rule)."""
     torch.manual_seed(0)
     model, fp, P = _model()
     B, res, n = 2, 16, 4
-    sched = CosineNoiseScheduler(1000).to(dev)
+    sched = LinearNoiseSchedule(1000).to(dev)
     smp = SimpleDDPMSampler(model, sched, EpsilonPredictionTransform(), DiffusionInputConfig("image", (res, res, 3), []))
     prior = torch.randn(B, res, res, 3)
     noises = [torch.randn(B, res, res, 3) for _ in range(n)]
     it = iter(noises)
     monkeypatch.setattr(utils, "device_normal", lambda key, shape, device, dtype=torch.float32: next(it).to(device))
-    out = smp.generate_samples(fp, B, res, diffusion_steps=n, start_step=1000, priors=prior, device=dev)
+    out = smp.generate_samples(fp, B, res, diffusion_steps=n, start_step=700, priors=prior, device=dev)
     freqs = model._fourier_freqs(dev).cpu()
-    steps = [float(s) for s in smp.get_steps(1000, 0, n)]
+    steps = [float(s) for s in smp.get_steps(700, 0, n)]
     x = prior.clone()
     for i, s in enumerate(steps):
         nxt = steps[i + 1] if i + 1 < n else 0.0

@@ -196,8 +196,11 @@ def test_dynamic_scale_training_matches_unscaled(graph, monkeypatch):
             assert tr.state.dynamic_scale.scale == 65536.0 and tr.state.dynamic_scale.fin_steps == 2
     assert abs(outs[0][0] - outs[1][0]) / outs[0][0] < 1e-3
     p0 = Unet(attention_configs=(None,) * 4).init(utils.split(utils.PRNGKey(4))[1], device=dev).flat
-    da, db = outs[0][1] - p0, outs[1][1] - p0
-    assert rel(da, db) < 5e-2            # bf16 activations + f32 atomics: same budget as the oracle comparison
+    da, db = (outs[0][1] - p0).double(), (outs[1][1] - p0).double()
+    # Adam's first steps are sign-like: elements whose gradient is ~0 flip with the f32-atomic summation order,
+    # so two RUNS of the same step differ element-wise; direction and magnitude of the update must agree
+    assert (da * db).sum() / (da.norm() * db.norm()) > 0.9
+    assert abs(da.norm() / db.norm() - 1) < 0.05
     assert rel(outs[0][2], outs[1][2]) < 1e-3
 
 
@@ -278,7 +281,7 @@ def test_ema_weights_stay_fresh_across_train_sample_train_sample():
                                      device=dev)
         assert rel(out, ref) < 2e-2, rnd
         outs.append(out)
-    assert len(smp._graphs) == 1                      # same graph replayed with refreshed weights
+    assert len(smp._graphs) == 2                      # (whole-step graph, last-step evaluation graph), both re-used
     assert rel(outs[0], outs[1]) > 1e-3               # the weights did change between the two samplings
 
 
@@ -300,7 +303,7 @@ def test_sampler_graph_cache_is_bounded_and_tree_params_are_packed_once():
         outs.append(smp.generate_samples(tree, B, res, diffusion_steps=2, start_step=1000,
                                          priors=torch.ones(B, res, res, 3, device=dev) * 40,
                                          model_conditioning_inputs=(cond,), device=dev))
-    assert len(smp._graphs) == 1 and len(smp._trees) == 1
+    assert len(smp._graphs) == 2 and len(smp._trees) == 1      # whole-step graph + last-step evaluation graph
     assert rel(outs[0], outs[1]) > 1e-4                        # conditioning really reaches the captured graph
     for i in range(8):                                         # different batch sizes: the LRU stays bounded
         smp.generate_samples(tree, 1 + i % 6, res, diffusion_steps=1, start_step=1000,
