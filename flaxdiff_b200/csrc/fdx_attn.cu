@@ -460,25 +460,27 @@ fdx_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(e_full);
     }
-    // epilogue: accumulators -> bf16 rows
+    // epilogue: accumulators -> bf16 rows.  tcgen05.ld is warp-collective (.sync.aligned): EVERY lane executes
+    // it, only the global stores are predicated on the row being inside the tensor.
     mbar_wait(done, 0);
     tc_fence_after();
-    if (r0 + row < nrows) {
-      constexpr int NOUT = ROWS_ARE_KEYS ? 2 : 1;
+    const bool row_ok = r0 + row < nrows;
+    constexpr int NOUT = ROWS_ARE_KEYS ? 2 : 1;
 #pragma unroll
-      for (int which = 0; which < NOUT; ++which) {
-        __nv_bfloat16* base;
-        if constexpr (ROWS_ARE_KEYS)
-          base = which == 0 ? p.dv + (long long)b * p.dv_bs + (long long)(r0 + row) * p.dv_ld
-                            : p.dk + (long long)b * p.dk_bs + (long long)(r0 + row) * p.dk_ld;
-        else
-          base = p.dq + (long long)b * p.dq_bs + (long long)(r0 + row) * p.dq_ld;
-        base += head * DH;
+    for (int which = 0; which < NOUT; ++which) {
+      __nv_bfloat16* base;
+      if constexpr (ROWS_ARE_KEYS)
+        base = which == 0 ? p.dv + (long long)b * p.dv_bs + (long long)(r0 + row) * p.dv_ld
+                          : p.dk + (long long)b * p.dk_bs + (long long)(r0 + row) * p.dk_ld;
+      else
+        base = p.dq + (long long)b * p.dq_bs + (long long)(r0 + row) * p.dq_ld;
+      base += head * DH;
 #pragma unroll
-        for (int c = 0; c < DH; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(lane_addr + 256u + (uint32_t)(which * 64 + c), v);
-          tmem_ld_wait();
+      for (int c = 0; c < DH; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_addr + 256u + (uint32_t)(which * 64 + c), v);
+        tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             uint4 u;

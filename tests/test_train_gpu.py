@@ -110,7 +110,10 @@ def test_apply_gradients_then_apply_ema_equals_fused_step():
     tree = {"params": {k: v for k, v in grads["params"].items()}}
     c = TrainState.create(model.apply, fp.clone(), fp.clone(), adamw(1e-3)).apply_gradients(grads=tree)
     d = TrainState.create(model.apply, fp.clone(), fp.clone(), adamw(1e-3)).apply_gradients(grads=grads)
-    assert torch.equal(c.params.flat, d.params.flat) and torch.equal(c.ema_params.flat, fp.flat)
+    # (compare the parameter TENSORS: `grads.flat` above also carries random values in the 64-element alignment
+    #  gaps between tensors, which a tree of leaves cannot)
+    assert all(torch.equal(c.params.named[k], d.params.named[k]) for k in c.params.named)
+    assert torch.equal(c.ema_params.flat, fp.flat)
 
 
 def test_dynamic_scale_step_semantics():
@@ -437,5 +440,5 @@ def test_train_step_parameters_and_ema_vs_oracle(graph, monkeypatch):
     assert abs((n_got / n_ref) ** 0.5 - 1) < 0.05            # update magnitude within 5 %
     assert (e_num / e_den) ** 0.5 < 0.45                     # EMA displacement tracks the oracle's
     full = tr.state.ema_params
-    for k in list(P)[:5]:
+    for k in [k for k in P if k.endswith("kernel")][:6]:     # (biases start at 0: their EMA IS the update)
         assert rel(full.named[k], ema[k]) < 1e-3             # absolute EMA values: tight
