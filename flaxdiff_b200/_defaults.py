@@ -8,7 +8,9 @@ ROUND2_DEFAULTS = {
     # name: (enabled, environment variable that selects the predecessor)
     "fused_attention": (True, "FDX_ATTN_UNFUSED"),     # fdx_attention_fwd/bwd vs separate QK^T / softmax / PV launches
     "wgrad9k": (True, "FDX_WGRAD9_V1"),                # ky-pairs-in-M weight gradient vs the round-1 nine-tap kernels
-    "gn_cluster_bwd": (True, "FDX_GN_2PASS"),          # one-launch cluster GroupNorm backward vs the two-pass one
+    # one-launch cluster GroupNorm backward vs the two-pass one: MEASURED SLOWER on B200 (profiles/layers_r02_gn_*.txt:
+    # 2.65 vs 1.81 ms over the C2 tensor set - fewer resident warps per SM cost more than the saved re-read), so off
+    "gn_cluster_bwd": (False, "FDX_GN_2PASS"),
     "dp_overlap": (True, "FDX_NO_DP_OVERLAP"),         # bucketed all-reduce inside the training graph vs one call after it
 }
 

@@ -1172,7 +1172,10 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
   // One-launch cluster path (x and dy read from HBM once): images of >= 1024 pixels.  The cluster size sets
   // both the parallelism per image and - with the shared-memory request that limits residency - how many
   // images are in flight; their x + dy must stay well inside the L2.  FDX_GN_2PASS=1 keeps the two-pass path.
-  static const bool two_pass = getenv("FDX_GN_2PASS") != nullptr;
+  static const bool two_pass = [] {          // set and not "0" (the round-2 default sets it: flaxdiff_b200/_defaults.py)
+    const char* e = getenv("FDX_GN_2PASS");
+    return e && e[0] && e[0] != '0';
+  }();
   const double img_bytes = 4.0 * HW * C;                      // x + dy of one image, bf16
   int CL = 8;
   while (CL > 1 && (HW / CL) < 4 * (kNT / (C / 8))) CL >>= 1;  // keep >= 4 row iterations per CTA
