@@ -11,7 +11,11 @@ ROUND2_DEFAULTS = {
     # one-launch cluster GroupNorm backward vs the two-pass one: MEASURED SLOWER on B200 (profiles/layers_r02_gn_*.txt:
     # 2.65 vs 1.81 ms over the C2 tensor set - fewer resident warps per SM cost more than the saved re-read), so off
     "gn_cluster_bwd": (False, "FDX_GN_2PASS"),
-    "dp_overlap": (True, "FDX_NO_DP_OVERLAP"),         # bucketed all-reduce inside the training graph vs one call after it
+    # bucketed all-reduce launched from the backward pass inside the training graph vs ONE fdx_comm call after it:
+    # MEASURED on 8 B200s (profiles/bench_r02_*_n8.json): C2 23.34 vs 23.11 ms/step, C3 91.0 vs 89.9 - the NCCL
+    # CTAs take SMs from the persistent one-CTA-per-SM tensor-core kernels, which then need a second wave; the
+    # exposed all-reduce (128 MB over NVSwitch) is only ~0.5 ms.  Overlap stays available (FDX_NO_DP_OVERLAP=0).
+    "dp_overlap": (False, "FDX_NO_DP_OVERLAP"),
 }
 
 

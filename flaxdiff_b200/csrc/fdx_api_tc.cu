@@ -251,6 +251,62 @@ int fdx_conv3x3_wgrad(const fdx_act* x, const fdx_act* dy, float* dw_hwio, int s
   return fdx_tc_launch(L, (cudaStream_t)stream);
 }
 
+// 1x1 convolution (the ResidualBlock's residual_conv, common.py:324-333) in CONVOLUTION geometry - one tap, no
+// shift - instead of as a flat GEMM: the launch is then eligible for the transposed engine (fdx_tct.cu, 256
+// pixels as N), which matters because these layers have few output columns and only K = Cin (forward) or
+// K = Cout (data gradient) = one or two 64-deep chunks, i.e. they are epilogue / bandwidth bound.
+int fdx_conv1x1_fwd(const fdx_act* x, const void* w_io, const float* bias, const fdx_act* res, const fdx_act* y,
+                    void* stream) {
+  int s;
+  if ((s = check_act(x, "conv1x1_fwd x")) != FDX_OK) return s;
+  if ((s = check_act(y, "conv1x1_fwd y")) != FDX_OK) return s;
+  FDX_REQUIRE(x->c % 64 == 0 && y->c % 64 == 0, "conv1x1_fwd: channels must be multiples of 64");
+  FDX_REQUIRE(y->n == x->n && y->h == x->h && y->w == x->w, "conv1x1_fwd: dims mismatch");
+  TcLaunch L{};
+  L.mode = TC_KMN;
+  fill_act_operand(L.A, x);
+  L.B.ptr = w_io;      // [Cin][Cout], Cout contiguous -> MN-major B
+  L.B.dims[0] = y->c; L.B.dims[1] = x->c; L.B.dims[2] = 1; L.B.dims[3] = 1;
+  L.B.strides[0] = 1; L.B.strides[1] = y->c; L.B.strides[2] = (uint64_t)x->c * y->c; L.B.strides[3] = L.B.strides[2];
+  L.W = y->w; L.H = y->h; L.N = y->n;
+  L.es = 1; L.ntaps = 1;
+  L.tap_dx[0] = 0; L.tap_dy[0] = 0; L.tap_b[0] = 0;
+  L.K = x->c; L.Ncols = y->c;
+  L.out = y->ptr;
+  L.os_x = y->pix_stride; L.os_y = y->pix_stride * y->w; L.os_n = y->pix_stride * y->w * y->h;
+  L.alpha = 1.f; L.bias = bias;
+  if (res) {
+    if ((s = check_act(res, "conv1x1_fwd res")) != FDX_OK) return s;
+    L.res = res->ptr;
+    L.rs_x = res->pix_stride; L.rs_y = res->pix_stride * res->w; L.rs_n = res->pix_stride * res->w * res->h;
+  }
+  return fdx_tc_launch(L, (cudaStream_t)stream);
+}
+
+int fdx_conv1x1_dgrad(const fdx_act* dy, const void* w_io, const fdx_act* dx, int accumulate, void* stream) {
+  int s;
+  if ((s = check_act(dy, "conv1x1_dgrad dy")) != FDX_OK) return s;
+  if ((s = check_act(dx, "conv1x1_dgrad dx")) != FDX_OK) return s;
+  FDX_REQUIRE(dx->c % 64 == 0 && dy->c % 64 == 0, "conv1x1_dgrad: channels must be multiples of 64");
+  FDX_REQUIRE(dx->n == dy->n && dx->h == dy->h && dx->w == dy->w, "conv1x1_dgrad: dims mismatch");
+  const int cin = dx->c, cout = dy->c;
+  TcLaunch L{};
+  L.mode = TC_KK;
+  fill_act_operand(L.A, dy);
+  L.B.ptr = w_io;      // [Cin][Cout] viewed as (k = Cout contiguous, n = Cin rows)
+  L.B.dims[0] = cout; L.B.dims[1] = cin; L.B.dims[2] = 1; L.B.dims[3] = 1;
+  L.B.strides[0] = 1; L.B.strides[1] = cout; L.B.strides[2] = (uint64_t)cin * cout; L.B.strides[3] = L.B.strides[2];
+  L.W = dx->w; L.H = dx->h; L.N = dx->n;
+  L.es = 1; L.ntaps = 1;
+  L.tap_dx[0] = 0; L.tap_dy[0] = 0; L.tap_b[0] = 0;
+  L.K = cout; L.Ncols = cin;
+  L.alpha = 1.f;
+  L.out = dx->ptr;
+  L.os_x = dx->pix_stride; L.os_y = dx->pix_stride * dx->w; L.os_n = dx->pix_stride * dx->w * dx->h;
+  if (accumulate) { L.res = dx->ptr; L.rs_x = L.os_x; L.rs_y = L.os_y; L.rs_n = L.os_n; }
+  return fdx_tc_launch(L, (cudaStream_t)stream);
+}
+
 int fdx_gemm(const fdx_gemm_desc* g, void* stream) {
   FDX_REQUIRE(g && g->A && g->B && g->D, "gemm: null pointer");
   FDX_REQUIRE(g->mode >= 0 && g->mode <= 2, "gemm: bad mode");

@@ -92,6 +92,25 @@ def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, dw_hwio: torch.Tensor, stri
     return dw_hwio
 
 
+def conv1x1_fwd(x: torch.Tensor, w_io: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                res: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """1x1 conv in convolution geometry: x NHWC bf16, w_io bf16 [Cin, Cout] (flax (1,1,Cin,Cout))."""
+    n, h, w, cin = x.shape
+    cout = w_io.shape[-1]
+    assert w_io.dtype == torch.bfloat16 and w_io.is_contiguous() and w_io.numel() == cin * cout
+    if out is None:
+        out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x.device)
+    check(load().fdx_conv1x1_fwd(ctypes.byref(act(x, "x")), ptr(w_io), ptr(bias), _opt_act(res, "res"),
+                                 ctypes.byref(act(out, "out")), stream_ptr()), "conv1x1_fwd")
+    return out
+
+
+def conv1x1_dgrad(dy: torch.Tensor, w_io: torch.Tensor, dx: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+    check(load().fdx_conv1x1_dgrad(ctypes.byref(act(dy, "dy")), ptr(w_io), ctypes.byref(act(dx, "dx")),
+                                   ctypes.c_int(1 if accumulate else 0), stream_ptr()), "conv1x1_dgrad")
+    return dx
+
+
 # --------------------------------------------------------------------------- gemm
 def gemm(mode: int, A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, M: int, N: int, K: int,
          a_ld: int, b_ld: int, d_ld: int, batch1: int = 1, batch2: int = 1,

@@ -81,6 +81,14 @@ int fdx_conv3x3_dgrad(const fdx_act* dy, const void* w_hwio, const fdx_act* dx, 
 int fdx_conv3x3_wgrad(const fdx_act* x, const fdx_act* dy, float* dw_hwio, int stride,
                       void* stream);
 
+/* 1x1 convolution in convolution geometry (ResidualBlock.residual_conv, models/common.py:324-333):
+ * y = x W + bias + res with W = [Cin][Cout] bf16 (flax (1,1,Cin,Cout) kernel), and its data gradient
+ * dx (+)= dy W^T.  Same arithmetic as fdx_gemm on the flattened pixels, but eligible for the transposed
+ * engine (few output columns, one or two K chunks: epilogue / bandwidth bound layers). */
+int fdx_conv1x1_fwd(const fdx_act* x, const void* w_io, const float* bias, const fdx_act* res, const fdx_act* y,
+                    void* stream);
+int fdx_conv1x1_dgrad(const fdx_act* dy, const void* w_io, const fdx_act* dx, int accumulate, void* stream);
+
 #define FDX_GEMM_KK 0   /* D[m][n] = sum_k A[m][k] * B[n][k]   (both k-contiguous)   */
 #define FDX_GEMM_KMN 1  /* D[m][n] = sum_k A[m][k] * B[k][n]                          */
 #define FDX_GEMM_MNMN 2 /* D[m][n] = sum_k A[k][m] * B[k][n]   (weight-gradient type) */
