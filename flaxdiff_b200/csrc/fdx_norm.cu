@@ -384,7 +384,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                     const __nv_bfloat16* __restrict__ dy, long long dps, int HW, int C, int G,
                     const float* __restrict__ stats, const float* __restrict__ red,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                    __nv_bfloat16* __restrict__ dx, long long dxps, float* __restrict__ csum_img) {
+                    __nv_bfloat16* __restrict__ dx, long long dxps, float* __restrict__ csum_img,
+                    const __nv_bfloat16* __restrict__ acc, long long accps) {
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
@@ -414,6 +415,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
     const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
     const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
     __nv_bfloat16* ob = dx + (long long)n * HW * dxps + cv * 8;
+    const __nv_bfloat16* ab_ = ACC ? acc + (long long)n * HW * accps + cv * 8 : nullptr;
     const int stride = gridDim.x * rows;
     for (int p0 = blockIdx.x * rows + r; p0 < HW; p0 += kBU * stride) {
       uint4 xu[kBU], du[kBU], ou[kBU];
@@ -426,7 +428,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
         if (p < HW) {
           xu[k] = *reinterpret_cast<const uint4*>(xb + (long long)p * xps);
           du[k] = *reinterpret_cast<const uint4*>(db_ + (long long)p * dps);
-          if (ACC) ou[k] = *reinterpret_cast<const uint4*>(ob + (long long)p * dxps);
+          if (ACC) ou[k] = *reinterpret_cast<const uint4*>(ab_ + (long long)p * accps);
         }
       }
 #pragma unroll
@@ -497,7 +499,7 @@ gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                       const __nv_bfloat16* __restrict__ dy, long long dps, int HW, int C, int G,
                       const float* __restrict__ stats, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float eps, float* __restrict__ ws,
-                      __nv_bfloat16* __restrict__ dx, long long dxps, float* __restrict__ csum_img) {
+                      __nv_bfloat16* __restrict__ dx, long long dxps, float* __restrict__ csum_img, const __nv_bfloat16* __restrict__ acc, long long accps) {
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const uint32_t CL = cluster_nctarank(), rank = cluster_ctarank();
   const int n = blockIdx.x / CL;
@@ -599,6 +601,7 @@ gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
 #pragma unroll
     for (int j = 0; j < 4; ++j) cs.v[j] = f2_pack(0.f, 0.f);
     __nv_bfloat16* ob = dx + (long long)n * HW * dxps + cv * 8;
+    const __nv_bfloat16* ab_ = ACC ? acc + (long long)n * HW * accps + cv * 8 : nullptr;
     for (int p0 = p_lo + r; p0 < p_hi; p0 += kBU * rows) {
       uint4 xu[kBU], du[kBU], ou[kBU];
 #pragma unroll
@@ -610,7 +613,7 @@ gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
         if (p < p_hi) {
           xu[k] = *reinterpret_cast<const uint4*>(xb + (long long)p * xps);
           du[k] = *reinterpret_cast<const uint4*>(db_ + (long long)p * dps);
-          if (ACC) ou[k] = *reinterpret_cast<const uint4*>(ob + (long long)p * dxps);
+          if (ACC) ou[k] = *reinterpret_cast<const uint4*>(ab_ + (long long)p * accps);
         }
       }
 #pragma unroll
@@ -674,7 +677,7 @@ gn_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ x, long long xps, const __n
                    const float* __restrict__ stats, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float eps, float* __restrict__ ws,
                    unsigned* __restrict__ counters, __nv_bfloat16* __restrict__ dx, long long dxps,
-                   float* __restrict__ csum_img) {
+                   float* __restrict__ csum_img, const __nv_bfloat16* __restrict__ acc, long long accps) {
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int tid = threadIdx.x;
   extern __shared__ float shm[];
@@ -814,6 +817,7 @@ gn_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ x, long long xps, const __n
         const __nv_bfloat16* xb = x + (long long)n * HW * xps + cv * 8;
         const __nv_bfloat16* db_ = dy + (long long)n * HW * dps + cv * 8;
         __nv_bfloat16* ob = dx + (long long)n * HW * dxps + cv * 8;
+        const __nv_bfloat16* ab_ = ACC ? acc + (long long)n * HW * accps + cv * 8 : nullptr;
         const int p_lo = (int)(seg - (long long)img * HW), p_hi = (int)(seg_hi - (long long)img * HW);
         for (int p0 = p_lo + r; p0 < p_hi; p0 += kBU * rows) {
           uint4 xu[kBU], du[kBU], ou[kBU];
@@ -826,7 +830,7 @@ gn_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ x, long long xps, const __n
             if (p < p_hi) {
               xu[k] = *reinterpret_cast<const uint4*>(xb + (long long)p * xps);
               du[k] = *reinterpret_cast<const uint4*>(db_ + (long long)p * dps);
-              if (ACC) ou[k] = *reinterpret_cast<const uint4*>(ob + (long long)p * dxps);
+              if (ACC) ou[k] = *reinterpret_cast<const uint4*>(ab_ + (long long)p * accps);
             }
           }
 #pragma unroll
@@ -883,7 +887,7 @@ gn_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ x, long long xps, const __n
 template <bool SILU, bool ACC, bool CS>
 int launch_bwd_pipe(const fdx_act* x, const fdx_act* dy, int groups, const float* stats, const float* gamma,
                     const float* beta, float eps, float* ws, unsigned* counters, int max_stages,
-                    const fdx_act* dx, float* csum_img, cudaStream_t st) {
+                    const fdx_act* dx, float* csum_img, const fdx_act* acc, cudaStream_t st) {
   const int C = x->c, HW = x->h * x->w, N = x->n;
   const size_t shm = sizeof(float) * (2 * (size_t)(kNT / (C / 8)) * C + 2 * groups);
   static int occ = 0;
@@ -915,7 +919,8 @@ int launch_bwd_pipe(const fdx_act* x, const fdx_act* dy, int groups, const float
   FDX_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_pipe_kernel<SILU, ACC, CS>, (const __nv_bfloat16*)x->ptr,
                               (long long)x->pix_stride, (const __nv_bfloat16*)dy->ptr, (long long)dy->pix_stride, N,
                               HW, C, groups, ips, stats, gamma, beta, eps, ws, counters, (__nv_bfloat16*)dx->ptr,
-                              (long long)dx->pix_stride, csum_img));
+                              (long long)dx->pix_stride, csum_img, (const __nv_bfloat16*)(acc ? acc->ptr : nullptr),
+                              (long long)(acc ? acc->pix_stride : 0)));
   fdx_count_launch();
   return FDX_OK;
 }
@@ -923,7 +928,7 @@ int launch_bwd_pipe(const fdx_act* x, const fdx_act* dy, int groups, const float
 template <bool SILU, bool ACC, bool CS>
 int launch_bwd_cluster(int CL, size_t shm, const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
                        const float* gamma, const float* beta, float eps, float* ws, const fdx_act* dx,
-                       float* csum_img, cudaStream_t st) {
+                       float* csum_img, const fdx_act* acc, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     FDX_CUDA(cudaFuncSetAttribute(gn_bwd_cluster_kernel<SILU, ACC, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -945,7 +950,8 @@ int launch_bwd_cluster(int CL, size_t shm, const fdx_act* x, const fdx_act* dy, 
   FDX_CUDA(cudaLaunchKernelEx(&cfg, gn_bwd_cluster_kernel<SILU, ACC, CS>, (const __nv_bfloat16*)x->ptr,
                               (long long)x->pix_stride, (const __nv_bfloat16*)dy->ptr, (long long)dy->pix_stride,
                               x->h * x->w, x->c, groups, stats, gamma, beta, eps, ws, (__nv_bfloat16*)dx->ptr,
-                              (long long)dx->pix_stride, csum_img));
+                              (long long)dx->pix_stride, csum_img, (const __nv_bfloat16*)(acc ? acc->ptr : nullptr),
+                              (long long)(acc ? acc->pix_stride : 0)));
   fdx_count_launch();
   return FDX_OK;
 }
@@ -1085,7 +1091,8 @@ dim3 gn_grid(const fdx_act* x, int unroll, int resident) {
 // second pass of the GroupNorm backward: template dispatch on (activation, accumulate, column sums)
 void launch_bwd_apply(const fdx_act* x, const fdx_act* dy, int groups, const float* stats, const float* red,
                       const float* gamma, const float* beta, float eps, int silu, const fdx_act* dx,
-                      int accumulate, float* csum_img, cudaStream_t st) {
+                      const fdx_act* acc, float* csum_img, cudaStream_t st) {
+  const int accumulate = acc != nullptr;
   const int C = x->c, HW = x->h * x->w;
   const size_t shm = csum_img ? sizeof(float) * (kNT / (C / 8)) * C : 0;
   const dim3 grid = gn_grid(x, kBU, accumulate ? 2 : 3);
@@ -1095,7 +1102,9 @@ void launch_bwd_apply(const fdx_act* x, const fdx_act* dy, int groups, const flo
 #define FDX_GN_APPLY(S, A, CSF)                                                                          \
   gn_bwd_apply_kernel<S, A, CSF><<<grid, kNT, shm, st>>>(xp, x->pix_stride, dp, dy->pix_stride, HW, C,  \
                                                          groups, stats, red, gamma, beta, eps, op,       \
-                                                         dx->pix_stride, csum_img)
+                                                         dx->pix_stride, csum_img,                                 \
+                                                         (const __nv_bfloat16*)(acc ? acc->ptr : nullptr),          \
+                                                         (long long)(acc ? acc->pix_stride : 0))
   const int key = (silu ? 4 : 0) | (accumulate ? 2 : 0) | (csum_img ? 1 : 0);
   switch (key) {
     case 0: FDX_GN_APPLY(false, false, false); break;
@@ -1154,10 +1163,11 @@ int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const 
   return FDX_OK;
 }
 
-int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
-                      const float* gamma, const float* beta, float eps, int silu, float* ws,
-                      float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
-                      float* csum_img, float* csum_tot, void* stream) {
+static int groupnorm_bwd_impl(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
+                              const float* gamma, const float* beta, float eps, int silu, float* ws,
+                              float* dgamma, float* dbeta, const fdx_act* dx, const fdx_act* acc,
+                              float* csum_img, float* csum_tot, void* stream) {
+  const int accumulate = acc != nullptr;
   int s = gn_check(x, groups, "groupnorm_bwd");
   if (s != FDX_OK) return s;
   FDX_REQUIRE(dy && dy->ptr && dx && dx->ptr && ws, "groupnorm_bwd: null tensor");
@@ -1192,7 +1202,7 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
     const int max_stages = 2 * N * groups;
     const int key = (silu ? 4 : 0) | (accumulate ? 2 : 0) | (csum_img ? 1 : 0);
     int rc;
-#define FDX_GN_PP(S, A, CSF) rc = launch_bwd_pipe<S, A, CSF>(x, dy, groups, stats, gamma, beta, eps, sums, counters, max_stages, dx, csum_img, st)
+#define FDX_GN_PP(S, A, CSF) rc = launch_bwd_pipe<S, A, CSF>(x, dy, groups, stats, gamma, beta, eps, sums, counters, max_stages, dx, csum_img, acc, st)
     switch (key) {
       case 0: FDX_GN_PP(false, false, false); break;
       case 1: FDX_GN_PP(false, false, true); break;
@@ -1226,7 +1236,7 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
     if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * N * C, st));
     const int key = (silu ? 4 : 0) | (accumulate ? 2 : 0) | (csum_img ? 1 : 0);
     int rc;
-#define FDX_GN_CL(S, A, CSF) rc = launch_bwd_cluster<S, A, CSF>(CL, shm, x, dy, groups, stats, gamma, beta, eps, sums, dx, csum_img, st)
+#define FDX_GN_CL(S, A, CSF) rc = launch_bwd_cluster<S, A, CSF>(CL, shm, x, dy, groups, stats, gamma, beta, eps, sums, dx, csum_img, acc, st)
     switch (key) {
       case 0: FDX_GN_CL(false, false, false); break;
       case 1: FDX_GN_CL(false, false, true); break;
@@ -1264,13 +1274,32 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
                                                    dbeta);
   FDX_LAUNCH_CHECK();
   if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * N * C, st));
-  launch_bwd_apply(x, dy, groups, stats, red, gamma, beta, eps, silu, dx, accumulate, csum_img, st);
+  launch_bwd_apply(x, dy, groups, stats, red, gamma, beta, eps, silu, dx, acc, csum_img, st);
   FDX_LAUNCH_CHECK();
   if (csum_tot) {
     reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(csum_img, N, C, csum_tot, 0);
     FDX_LAUNCH_CHECK();
   }
   return FDX_OK;
+}
+
+int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
+                      const float* gamma, const float* beta, float eps, int silu, float* ws,
+                      float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
+                      float* csum_img, float* csum_tot, void* stream) {
+  return groupnorm_bwd_impl(x, dy, groups, stats, gamma, beta, eps, silu, ws, dgamma, dbeta, dx,
+                            accumulate ? dx : nullptr, csum_img, csum_tot, stream);
+}
+
+int fdx_groupnorm_bwd_add(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
+                          const float* gamma, const float* beta, float eps, int silu, float* ws,
+                          float* dgamma, float* dbeta, const fdx_act* dx, const fdx_act* addend,
+                          float* csum_img, float* csum_tot, void* stream) {
+  FDX_REQUIRE(addend && addend->ptr, "groupnorm_bwd_add: null addend");
+  FDX_REQUIRE(addend->c == x->c && addend->n == x->n && addend->h == x->h && addend->w == x->w,
+              "groupnorm_bwd_add: addend shape mismatch");
+  return groupnorm_bwd_impl(x, dy, groups, stats, gamma, beta, eps, silu, ws, dgamma, dbeta, dx, addend, csum_img,
+                            csum_tot, stream);
 }
 
 int fdx_groupnorm_coeffs(const float* stats, const float* gamma, const float* beta, int N, int HW, int C,
@@ -1310,7 +1339,7 @@ int fdx_groupnorm_bwd_dz(const fdx_act* x, const fdx_act* dz, int groups, const 
   FDX_LAUNCH_CHECK();
   if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * N * C, st));
   // dz already carries silu'(z): the second pass is the activation-free one (beta is not read)
-  launch_bwd_apply(x, dz, groups, stats, red, gamma, gamma, eps, 0, dx, accumulate, csum_img, st);
+  launch_bwd_apply(x, dz, groups, stats, red, gamma, gamma, eps, 0, dx, accumulate ? dx : nullptr, csum_img, st);
   FDX_LAUNCH_CHECK();
   if (csum_tot) {
     reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(csum_img, N, C, csum_tot, 0);

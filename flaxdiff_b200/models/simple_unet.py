@@ -1007,18 +1007,32 @@ class Unet:
             side.keep.append(drow16)
             ops.conv3x3_wgrad(a1, dh, Gd[f"{name}/conv1/conv/kernel"])
         side.run(conv1_param_grads, dh, drow)
-        # conv1 data gradient -> norm1 + silu backward -> dx
+        # conv1 data gradient -> norm1 + silu backward -> dx, joined with the skip gradient (out = h + residual,
+        # common.py:334-336) WITHOUT a separate read-modify-write pass over dx:
+        #   1x1 residual conv : its data gradient is written (or accumulated) into dx FIRST - a plain store when dx is
+        #                       fresh - and the GroupNorm backward adds on top (reads dx at HBM speed instead of
+        #                       the GEMM epilogue re-reading it);
+        #   identity residual : the GroupNorm backward takes dout as its addend (no act_add launch).
         dx, acc = want(xin)
-        ops.conv_dgrad_groupnorm_bwd(dh, W16[f"{name}/conv1/conv/kernel"], x, G, st1,
-                                     W[f"{name}/{self._n1}/scale"], W[f"{name}/{self._n1}/bias"], RES_EPS,
-                                     Gd[f"{name}/{self._n1}/scale"], Gd[f"{name}/{self._n1}/bias"], dx, acc)
-        del dh
-        # residual path
-        if cin != cout:
+        gn1 = (dh, W16[f"{name}/conv1/conv/kernel"], x, G, st1, W[f"{name}/{self._n1}/scale"],
+               W[f"{name}/{self._n1}/bias"], RES_EPS, Gd[f"{name}/{self._n1}/scale"], Gd[f"{name}/{self._n1}/bias"], dx)
+        if os.environ.get("FDX_RES_BWD_V1"):        # round-1 order (GroupNorm backward, then the residual pass)
+            ops.conv_dgrad_groupnorm_bwd(*gn1, acc)
+            if cin != cout:
+                ops.gemm(GEMM_KK, dout, W16[kres + "kernel"].view(cin, cout), dx, M, cin, cout, dout.stride(2), cout,
+                         dx.stride(2), res=dx, r_ld=dx.stride(2))
+            else:
+                ops.act_add(dx, dout, dx)
+        elif cin != cout:
             ops.gemm(GEMM_KK, dout, W16[kres + "kernel"].view(cin, cout), dx, M, cin, cout, dout.stride(2), cout,
-                     dx.stride(2), res=dx, r_ld=dx.stride(2))
-        else:
+                     dx.stride(2), res=dx if acc else None, r_ld=dx.stride(2) if acc else 0)
+            ops.conv_dgrad_groupnorm_bwd(*gn1, True)
+        elif acc:
+            ops.conv_dgrad_groupnorm_bwd(*gn1, True)
             ops.act_add(dx, dout, dx)
+        else:
+            ops.conv_dgrad_groupnorm_bwd(*gn1, False, addend=dout)
+        del dh
 
     def _attn_bwd(self, rec, W, W16, Gd, want, grad_of):
         """Backward of _attn_fwd: projection GEMMs around fdx_attention_bwd (dQ / dK / dV with the logits

@@ -167,8 +167,18 @@ def groupnorm_apply(x, groups, stats, gamma, beta, eps: float, silu: bool, out=N
 
 
 def groupnorm_bwd(x, dy, groups, stats, gamma, beta, eps, silu, dgamma, dbeta, dx,
-                  accumulate: bool = False, csum_img=None, csum_tot=None) -> torch.Tensor:
+                  accumulate: bool = False, csum_img=None, csum_tot=None, addend=None) -> torch.Tensor:
+    """dx (+)= d/dx GroupNorm(+SiLU); `addend`: dx = d/dx + addend (another tensor of the same shape)."""
     red = torch.empty(2 * x.shape[0] * (x.shape[-1] + groups), dtype=torch.float32, device=x.device)
+    if addend is not None:
+        assert not accumulate
+        check(load().fdx_groupnorm_bwd_add(ctypes.byref(act(x, "x")), ctypes.byref(act(dy, "dy")),
+                                           ctypes.c_int(groups), ptr(stats), ptr(gamma), ptr(beta),
+                                           ctypes.c_float(eps), ctypes.c_int(1 if silu else 0), ptr(red),
+                                           ptr(dgamma), ptr(dbeta), ctypes.byref(act(dx, "dx")),
+                                           ctypes.byref(act(addend, "addend")), ptr(csum_img), ptr(csum_tot),
+                                           stream_ptr()), "groupnorm_bwd_add")
+        return dx
     check(load().fdx_groupnorm_bwd(ctypes.byref(act(x, "x")), ctypes.byref(act(dy, "dy")),
                                    ctypes.c_int(groups), ptr(stats), ptr(gamma), ptr(beta),
                                    ctypes.c_float(eps), ctypes.c_int(1 if silu else 0), ptr(red),
@@ -220,7 +230,7 @@ def groupnorm_bwd_dz(x, dz, groups, stats, gamma, eps, ws_slots, dgamma, dbeta, 
 
 def conv_dgrad_groupnorm_bwd(dy, w_hwio, x, groups, stats, gamma, beta, eps, dgamma, dbeta, dx,
                              accumulate: bool = False, csum_img=None, csum_tot=None,
-                             fused: Optional[bool] = None) -> torch.Tensor:
+                             fused: Optional[bool] = None, addend=None) -> torch.Tensor:
     """d/dx of conv3x3(silu(groupnorm(x))) given dy = d/d(conv output): data gradient, then the two-pass
     GroupNorm backward.  FDX_GN_FUSE=1 selects the fused dgrad epilogue instead (parity-tested, but
     measured slower on B200 except when Cout >= 2 Cin: one epilogue warp per scheduler cannot hide the
@@ -228,14 +238,14 @@ def conv_dgrad_groupnorm_bwd(dy, w_hwio, x, groups, stats, gamma, beta, eps, dga
     da = torch.empty(tuple(x.shape), dtype=torch.bfloat16, device=x.device)
     if fused is None:
         fused = bool(os.environ.get("FDX_GN_FUSE"))
-    if fused and x.shape[1] * x.shape[2] >= GN_FUSE_MIN_PIXELS:
+    if fused and addend is None and x.shape[1] * x.shape[2] >= GN_FUSE_MIN_PIXELS:
         ab = groupnorm_coeffs(stats, gamma, beta, x.shape[1] * x.shape[2], eps)
         ws = conv3x3_dgrad_gn(dy, w_hwio, da, x, ab)
         return groupnorm_bwd_dz(x, da, groups, stats, gamma, eps, ws, dgamma, dbeta, dx, accumulate,
                                 csum_img=csum_img, csum_tot=csum_tot)
     conv3x3_dgrad(dy, w_hwio, da)
     return groupnorm_bwd(x, da, groups, stats, gamma, beta, eps, True, dgamma, dbeta, dx, accumulate,
-                         csum_img=csum_img, csum_tot=csum_tot)
+                         csum_img=csum_img, csum_tot=csum_tot, addend=addend)
 
 
 def rmsnorm_fwd(x, scale, eps: float, out=None) -> torch.Tensor:

@@ -140,6 +140,12 @@ int fdx_groupnorm_bwd(const fdx_act* x, const fdx_act* dy, int groups, const flo
                       const float* gamma, const float* beta, float eps, int silu, float* ws,
                       float* dgamma, float* dbeta, const fdx_act* dx, int accumulate,
                       float* csum_img, float* csum_tot, void* stream);
+/* Same, with the result ADDED to another tensor: dx = d/dx + addend (addend may be dx itself = accumulate).  The
+ * ResidualBlock's skip gradient (common.py:334-336: out + residual) joins here instead of in a separate pass. */
+int fdx_groupnorm_bwd_add(const fdx_act* x, const fdx_act* dy, int groups, const float* stats,
+                          const float* gamma, const float* beta, float eps, int silu, float* ws,
+                          float* dgamma, float* dbeta, const fdx_act* dx, const fdx_act* addend,
+                          float* csum_img, float* csum_tot, void* stream);
 /* Fused variant of the backward above: the data-gradient convolution that PRODUCES dy applies
  * silu'(z) in its epilogue and accumulates the first-pass sums, so x and dy are read once less.
  *   fdx_groupnorm_coeffs : ab[n][0][c] = rstd*gamma_c, ab[n][1][c] = beta_c - mean*rstd*gamma_c

@@ -54,6 +54,13 @@ def test_groupnorm_fwd_bwd(shape, silu):
     dg.zero_(); db.zero_()
     ops.groupnorm_bwd(x, dy, 8, st, gamma, beta, 1e-4, silu, dg, db, dx2, accumulate=True)
     assert rel(dx2, xr.grad + base.float().cpu()) < 1e-2
+    # addend from ANOTHER tensor (the ResidualBlock's skip gradient joins inside the kernel), itself a strided slot
+    wide = torch.randn(B, H, W, C + 64, device=dev).bfloat16()
+    add = wide[..., 64:]
+    dx3 = torch.empty_like(dx)
+    dg.zero_(); db.zero_()
+    ops.groupnorm_bwd(x, dy, 8, st, gamma, beta, 1e-4, silu, dg, db, dx3, addend=add)
+    assert rel(dx3, xr.grad + add.float().cpu()) < 1e-2
     if H * W >= 1024:      # the two-pass path (FDX_GN_2PASS is read once per process: compare via the 2x smaller image rule)
         assert rel(dg, gr.grad) < 5e-3 and rel(db, br.grad) < 5e-3
 
