@@ -42,13 +42,20 @@ struct TctDev {
   int cs_slots, cs_ld;
 };
 
-template <int MT, bool A_MN>
+// HALO = true (round 2, 3x3 stride-1 only): the 64- and 128-output-channel layers were L2 -> shared-memory
+// bandwidth bound, not MMA bound: every (tap, K chunk) re-loaded its 256 pixels, 40 KB of TMA per 2.1 MFLOP at
+// M = 64 = 52 FLOP per byte, and the L2 delivers ~15 TB/s (780 TF/s measured on 64 -> 64).  Here ONE tall box of
+// 16 x 18 pixels (rows y0-1 .. y0+16) is loaded per (kx, K chunk); the three ky taps are 2048-byte row offsets
+// into it (swizzle-aligned views, exactly as in the nine-tap weight gradient), so a stage carries three weight
+// tiles + 36 KB of pixels and feeds twelve MMAs: 96 -> 36 KB of pixel traffic per three taps.
+template <int MT, bool A_MN, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
                const TctDev p) {
   constexpr int kWBytes = MT * 128;                       // MT channels x 64 k
-  constexpr int kStageBytes = kWBytes + kPixBytes;
-  constexpr int S = (MT == 128) ? 4 : 5;
+  constexpr int kHaloBytes = 18 * 16 * 128;               // 16 x 18 pixel box
+  constexpr int kStageBytes = HALO ? (3 * kWBytes + kHaloBytes) : (kWBytes + kPixBytes);
+  constexpr int S = HALO ? ((MT == 128) ? 2 : 3) : ((MT == 128) ? 4 : 5);
   constexpr bool IL = (MT == 64);                         // two interleaved pixel halves per tile
   constexpr int NH = IL ? 2 : 1;
   constexpr int TH = 16 * NH;                             // pixel rows per tile
@@ -86,6 +93,31 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         const int mt = tile / p.cblks;
         const int xb = mt % p.nxb, yb = (mt / p.nxb) % p.nyb, nb = mt / (p.nxb * p.nyb);
         const int x0 = xb * 16;
+        if constexpr (HALO) {
+          // stages: (kx, K chunk, half); taps t = ky * 3 + kx (fdx_conv3x3_fwd / dgrad fill order)
+          for (int qq = 0; qq < 3 * p.kchunks * NH; ++qq) {
+            const int q = qq / NH, y0 = yb * TH + 16 * (qq % NH);
+            const int kx = q / p.kchunks, kc = q % p.kchunks;
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sw = smem + stage * kStageBytes;
+            uint8_t* sx = sw + 3 * kWBytes;
+            mbar_arrive_expect_tx(&full[stage], kStageBytes);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const int t = ky * 3 + kx;
+              if constexpr (A_MN) {
+#pragma unroll
+                for (int j = 0; j < MT / 64; ++j)
+                  tma_load_4d(sw + ky * kWBytes + j * 8192, &mapW, &full[stage], cb * MT + j * 64,
+                              p.tap_b[t] + kc * 64, 0, 0);
+              } else {
+                tma_load_4d(sw + ky * kWBytes, &mapW, &full[stage], kc * 64, cb * MT, p.tap_b[t], 0);
+              }
+            }
+            tma_load_4d(sx, &mapX, &full[stage], kc * 64, x0 + kx - 1, y0 - 1, nb);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        } else
         for (int qq = 0; qq < nk * NH; ++qq) {
           const int q = qq / NH, y0 = yb * TH + 16 * (qq % NH);
           const int t = q / p.kchunks, kc = q % p.kchunks;
@@ -116,6 +148,27 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        if constexpr (HALO) {
+          for (int qq = 0; qq < 3 * p.kchunks * NH; ++qq) {
+            const uint32_t dh = d_tmem + ((uint32_t)((qq % NH) * 16) << 16);
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sw = smem_u32(smem + stage * kStageBytes);
+            const uint32_t sx = sw + 3 * kWBytes;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = A_MN ? umma_desc_sw128(sw + ky * kWBytes + k * 2048, 8192, 1024)
+                                         : umma_desc_sw128(sw + ky * kWBytes + k * 32, 16, 1024);
+                const uint64_t db = umma_desc_sw128(sx + ky * 2048 + k * 32, 16, 1024);   // rows ky .. ky+15 of the box
+                umma_f16(dh, da, db, idesc, (qq >= NH || ky != 0 || k != 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        } else
         for (int qq = 0; qq < nk * NH; ++qq) {
           const int q = qq / NH;
           const uint32_t dh = d_tmem + ((uint32_t)((qq % NH) * 16) << 16);   // half 1 -> TMEM lanes 16..31
@@ -263,19 +316,20 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-template <int MT, bool A_MN>
+template <int MT, bool A_MN, bool HALO>
 int launch_tct(const CUtensorMap& mW, const CUtensorMap& mX, const TctDev& d, cudaStream_t stream) {
-  constexpr int S = (MT == 128) ? 4 : 5;
-  constexpr int smem = S * (MT * 128 + kPixBytes) + 1024 + 256 + 20480 /* epilogue transpose tiles */;
+  constexpr int S = HALO ? ((MT == 128) ? 2 : 3) : ((MT == 128) ? 4 : 5);
+  constexpr int stage = HALO ? (3 * MT * 128 + 18 * 16 * 128) : (MT * 128 + kPixBytes);
+  constexpr int smem = S * stage + 1024 + 256 + 20480 /* epilogue transpose tiles */;
   static bool attr_set = false;
   if (!attr_set) {
-    FDX_CUDA(cudaFuncSetAttribute(fdx_tct_kernel<MT, A_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FDX_CUDA(cudaFuncSetAttribute(fdx_tct_kernel<MT, A_MN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   int grid = fdx_num_sms();
   if (grid <= 0) return FDX_ERR_NO_DEVICE;
   if (d.ntiles < grid) grid = d.ntiles;
-  fdx_tct_kernel<MT, A_MN><<<grid, kThreads, smem, stream>>>(mW, mX, d);
+  fdx_tct_kernel<MT, A_MN, HALO><<<grid, kThreads, smem, stream>>>(mW, mX, d);
   fdx_note_kernel(FDX_KERNEL_TCT);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
@@ -304,12 +358,19 @@ int fdx_tct_launch(const TcLaunch& L, cudaStream_t stream) {
   d.res = L.res; d.rs_x = L.rs_x; d.rs_y = L.rs_y; d.rs_n = L.rs_n;
   d.cs_ws = L.gn_ws; d.cs_slots = L.gn_slots > 0 ? L.gn_slots : 1; d.cs_ld = L.ws_ld > 0 ? L.ws_ld : L.Ncols;
 
+  // halo-sharing variant: standard 3x3 stride-1 tap set in (ky, kx) order.  FDX_TCT_HALO=0 disables it,
+  // FDX_TCT_HALO=64 / 128 restricts it to that M tile.
+  bool halo = L.ntaps == 9;
+  for (int t = 0; t < 9 && halo; ++t) halo = (L.tap_dx[t] == t % 3 - 1) && (L.tap_dy[t] == t / 3 - 1);
+  const char* he = getenv("FDX_TCT_HALO");          // read per launch: the A/B tests toggle it in-process
+  const int halo_env = (he && *he) ? atoi(he) : -1;
+  if (halo_env == 0 || (halo_env > 0 && halo_env != MT)) halo = false;
   CUtensorMap mW, mX;
   {
     uint64_t dims[4], str[3];
     for (int i = 0; i < 4; ++i) dims[i] = L.A.dims[i];
     for (int i = 1; i < 4; ++i) str[i - 1] = L.A.strides[i] * 2;
-    uint32_t box[4] = {64, 16, 8, 1};
+    uint32_t box[4] = {64, 16, (uint32_t)(halo ? 18 : 8), 1};
     uint32_t est[4] = {1, 1, 1, 1};
     int s = fdx_make_tmap_bf16(&mX, L.A.ptr, 4, dims, str, box, est, 1);
     if (s != FDX_OK) return s;
@@ -323,6 +384,9 @@ int fdx_tct_launch(const TcLaunch& L, cudaStream_t stream) {
     int s = fdx_make_tmap_bf16(&mW, L.B.ptr, 4, dims, str, box, est, 1);
     if (s != FDX_OK) return s;
   }
-  if (L.mode == TC_KMN) return MT == 128 ? launch_tct<128, true>(mW, mX, d, stream) : launch_tct<64, true>(mW, mX, d, stream);
-  return MT == 128 ? launch_tct<128, false>(mW, mX, d, stream) : launch_tct<64, false>(mW, mX, d, stream);
+#define FDX_TCT_GO(M_, AMN_)                                                                   \
+  (halo ? launch_tct<M_, AMN_, true>(mW, mX, d, stream) : launch_tct<M_, AMN_, false>(mW, mX, d, stream))
+  if (L.mode == TC_KMN) return MT == 128 ? FDX_TCT_GO(128, true) : FDX_TCT_GO(64, true);
+  return MT == 128 ? FDX_TCT_GO(128, false) : FDX_TCT_GO(64, false);
+#undef FDX_TCT_GO
 }

@@ -54,6 +54,32 @@ def _conv_ref(x, w, b=None, res=None):
 SHAPES = [(2, 32, 32, 128, 256), (2, 32, 32, 256, 128), (4, 16, 16, 64, 64), (1, 64, 64, 64, 128), (2, 16, 16, 320, 192)]
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout", SHAPES + [(2, 48, 32, 64, 192), (1, 16, 16, 128, 320), (3, 32, 16, 384, 64)])
+def test_transposed_engine_halo_sharing_vs_per_tap_loads(B, H, W, cin, cout):
+    """fdx_tct_kernel<.., HALO=true> (one 16 x 18 pixel box per (kx, K chunk), ky taps as row-offset views)
+    against the round-1 per-tap loads (FDX_TCT_HALO=0): bit-identical outputs are NOT expected (the taps are
+    accumulated in a different order), both must match fp32 torch."""
+    torch.manual_seed(0)
+    x = torch.randn(B, H, W, cin, device=dev).bfloat16()
+    w = (torch.randn(3, 3, cin, cout, device=dev) / (3 * cin ** 0.5)).bfloat16()
+    bias = torch.randn(cout, device=dev)
+    res = torch.randn(B, H, W, cout, device=dev).bfloat16()
+    dy = torch.randn(B, H, W, cout, device=dev).bfloat16()
+    want = _conv_ref(x, w, bias, res)
+    xr = x.float().clone().requires_grad_(True)
+    _conv_ref(xr, w).backward(dy.float())
+    outs = []
+    for halo in ("0", None):
+        with env(FDX_TCT_HALO=halo):
+            y = ops.conv3x3_fwd(x, w, bias, res=res)
+            dx = torch.empty_like(x)
+            ops.conv3x3_dgrad(dy, w, dx)
+            torch.cuda.synchronize()
+        assert rel(y, want) < 5e-3 and rel(dx, xr.grad) < 5e-3, halo
+        outs.append((y, dx))
+    assert rel(outs[1][0], outs[0][0]) < 2e-3 and rel(outs[1][1], outs[0][1]) < 2e-3
+
+
 @pytest.mark.parametrize("flag", ["FDX_PAIR", "FDX_CONV3", "FDX_NO_TCT"])
 @pytest.mark.parametrize("B,H,W,cin,cout", SHAPES)
 def test_forward_and_dgrad_variants(flag, B, H, W, cin, cout):
