@@ -324,6 +324,12 @@ def profile_kernels(trainer, images, noise, t, ctx=None):
     orig = {n: getattr(ops, n) for n in table}
     recs = []
 
+    def shape_of(name, a, k):
+        if name == "gemm":
+            return f"M={a[4]} N={a[5]} K={a[6]} mode={a[0]} batch={k.get('batch1', 1)}x{k.get('batch2', 1)}"
+        ts = [tuple(x.shape) for x in a[:4] if hasattr(x, "shape") and x.dim() == 4]
+        return " ".join("x".join(map(str, t)) for t in ts[:2]) + (f" s{k['stride']}" if k.get("stride", 1) != 1 else "")
+
     def wrap(name, fn):
         def inner(*a, **k):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -331,7 +337,7 @@ def profile_kernels(trainer, images, noise, t, ctx=None):
             r = fn(*a, **k)
             e.record()
             kind = lib.fdx_last_kernel_kind()
-            recs.append((s, e, table[name](a, k), kind, name))
+            recs.append((s, e, table[name](a, k), kind, name, shape_of(name, a, k)))
             return r
         return inner
     saved_env = {k: os.environ.get(k) for k in ("FDX_MICROBATCH", "FDX_NO_SIDE")}
@@ -355,12 +361,21 @@ def profile_kernels(trainer, images, noise, t, ctx=None):
             else:
                 os.environ[k] = v
     kinds = {}
-    for s, e, fl, kind, name in recs:
+    dump = os.environ.get("FDX_BENCH_CALLS")          # per-call table (op, shape, kernel, ms, TFLOP/s) for profiles/
+    rows = []
+    for s, e, fl, kind, name, shp in recs:
         kname = lib.fdx_kernel_kind_name(kind).decode()
+        if dump:
+            ms = s.elapsed_time(e)
+            rows.append(f"{name:16s} {shp:44s} {kname:20s} {ms * 1e3:9.1f} us {fl / 1e9:9.1f} GF "
+                        f"{fl / max(ms, 1e-6) / 1e9:8.1f} TF/s")
         d = kinds.setdefault(kname, {"calls": 0, "ms": 0.0, "gflop": 0.0})
         d["calls"] += 1
         d["ms"] += s.elapsed_time(e)
         d["gflop"] += fl / 1e9
+    if dump:
+        with open(dump, "w") as f:
+            f.write("\n".join(rows) + "\n")
     return kinds
 
 

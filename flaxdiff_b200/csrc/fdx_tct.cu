@@ -97,6 +97,7 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           // stages: (kx, K chunk, half); taps t = ky * 3 + kx (fdx_conv3x3_fwd / dgrad fill order)
           for (int qq = 0; qq < 3 * p.kchunks * NH; ++qq) {
             const int q = qq / NH, y0 = yb * TH + 16 * (qq % NH);
+            if (IL && y0 >= p.H) continue;          // H % 32 == 16: the last tile has no second half
             const int kx = q / p.kchunks, kc = q % p.kchunks;
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sw = smem + stage * kStageBytes;
@@ -120,6 +121,7 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         } else
         for (int qq = 0; qq < nk * NH; ++qq) {
           const int q = qq / NH, y0 = yb * TH + 16 * (qq % NH);
+          if (IL && y0 >= p.H) continue;            // H % 32 == 16: the last tile has no second half
           const int t = q / p.kchunks, kc = q % p.kchunks;
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sw = smem + stage * kStageBytes;
@@ -148,8 +150,10 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        const int yb_i = ((tile / p.cblks) / p.nxb) % p.nyb;
         if constexpr (HALO) {
           for (int qq = 0; qq < 3 * p.kchunks * NH; ++qq) {
+            if (IL && yb_i * TH + 16 * (qq % NH) >= p.H) continue;   // same skip as the producer
             const uint32_t dh = d_tmem + ((uint32_t)((qq % NH) * 16) << 16);
             mbar_wait(&full[stage], phase);
             tc_fence_after();
@@ -171,6 +175,7 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         } else
         for (int qq = 0; qq < nk * NH; ++qq) {
           const int q = qq / NH;
+          if (IL && yb_i * TH + 16 * (qq % NH) >= p.H) continue;     // same skip as the producer
           const uint32_t dh = d_tmem + ((uint32_t)((qq % NH) * 16) << 16);   // half 1 -> TMEM lanes 16..31
           mbar_wait(&full[stage], phase);
           tc_fence_after();
