@@ -264,10 +264,14 @@ def kernel_traffic(workload: str, kernel: str):
     pass of the same workload (profiles/roofline_traffic.json, written by profiles/summarize_metrics.py)."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            rec = json.load(f).get(workload, {}).get("kernels", {}).get(kernel)
-        if rec:
-            return {"traffic": rec["dram_bytes_per_launch"], "traffic_unit": "DRAM bytes per launch (ncu)",
-                    "traffic_launches": rec["launches"], "traffic_source": rec["source"]}
+            kern = json.load(f).get(workload, {}).get("kernels", {})
+        # the ncu names carry the template arguments ("fdx_tc_kernel<256, 1, 2, 0>"): all instantiations of the family
+        recs = [v for k, v in kern.items() if k == kernel or k.startswith(kernel + "<")]
+        n = sum(r["launches"] for r in recs)
+        if n:
+            return {"traffic": sum(r["dram_bytes_per_launch"] * r["launches"] for r in recs) / n,
+                    "traffic_unit": "DRAM bytes per launch (ncu, mean over the family's launches in one step)",
+                    "traffic_launches": n, "traffic_source": recs[0]["source"]}
     except Exception:  # noqa: BLE001
         pass
     return {"traffic": None}

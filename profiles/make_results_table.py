@@ -1,5 +1,6 @@
 """Markdown results tables from the committed bench lines (profiles/bench_rNN_*.json).
-usage: python profiles/make_results_table.py [r02]
+usage: python profiles/make_results_table.py [r02] [--readme]   (--readme: rewrite the block between the
+<!-- results:begin --> / <!-- results:end --> markers of README.md)
 One row per block of every line: the headline (C2 training), `sample`, `train_256`, `sample_256_heun`,
 `sample_256_text_cfg` of the default run, plus single-workload and multi-GPU lines when present."""
 import glob
@@ -8,7 +9,13 @@ import os
 import sys
 
 here = os.path.dirname(os.path.abspath(__file__))
-rnd = sys.argv[1] if len(sys.argv) > 1 else "r02"
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+rnd = argv[0] if argv else "r02"
+out = []
+
+
+def emit(line=""):
+    out.append(line)
 
 
 def last_json(path):
@@ -58,13 +65,21 @@ for f in sorted(glob.glob(os.path.join(here, f"bench_{rnd}_*.json"))):
             sample.append((tag, f"{d['config']['sampler']} {r['diffusion_steps']} steps, B={d['config']['batch_per_gpu']}",
                            f"{r['denoise_steps_per_sec']:.1f}", f"{r['image_steps_per_sec']:.0f}",
                            f"{r['tensor_frac_of_sustained']:.3f}"))
-print("| line | workload | value (device-resident) | ms/step | e2e img/s | whole-step frac of sustained bf16 | "
+emit("| line | workload | value (device-resident) | ms/step | e2e img/s | whole-step frac of sustained bf16 | "
       "dominant kernel: frac of sustained bf16 | launches/step |")
-print("|---|---|---|---|---|---|---|---|")
+emit("|---|---|---|---|---|---|---|---|")
 for r in train:
-    print("| " + " | ".join(r) + " |")
-print()
-print("| line | sampler | denoise steps/s | image-steps/s (all GPUs) | UNet FLOPs frac of sustained bf16 |")
-print("|---|---|---|---|---|")
+    emit("| " + " | ".join(r) + " |")
+emit()
+emit("| line | sampler | denoise steps/s | image-steps/s (all GPUs) | UNet FLOPs frac of sustained bf16 |")
+emit("|---|---|---|---|---|")
 for r in sample:
-    print("| " + " | ".join(r) + " |")
+    emit("| " + " | ".join(r) + " |")
+text = "\n".join(out)
+if "--readme" in sys.argv:
+    readme = os.path.join(os.path.dirname(here), "README.md")
+    doc = open(readme).read()
+    a, b = doc.index("<!-- results:begin -->"), doc.index("<!-- results:end -->")
+    open(readme, "w").write(doc[:a] + "<!-- results:begin -->\n" + text + "\n" + doc[b:])
+else:
+    print(text)
