@@ -469,7 +469,8 @@ def run_train(D, args, workload, steps, warmup, with_cpu_baseline):
                        "parallelism": f"dp{world}", "params": model.layout().num_params,
                        "cuda_graph": not args.no_graph,
                        "grad_exchange": (f"fdx_comm_allreduce_avg x{len(trainer._exchange.bounds)} buckets, "
-                                         f"{'overlapped with backward' if trainer._overlap else 'after backward'}")
+                                         "overlapped with backward" if trainer._overlap else
+                                         "one fdx_comm_allreduce_avg (gradient + loss) after backward")
                        if trainer._exchange is not None else "none (single GPU)",
                        "l2": "per-step activation traffic (>= 9 GB) exceeds the 126 MB L2; no explicit flush needed"},
             "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "images/s", "ms_per_step": ms_e2e,

@@ -77,17 +77,35 @@ __device__ __forceinline__ void store_p_chunk(uint32_t sP, int r, int c0, const 
 // SHORT = the keys fit one 128-key block (77 text tokens): no ring, one P tile, 256 TMEM columns and 80 KB of
 // shared memory, so TWO CTAs share an SM - with L/128 x heads x B short-lived CTAs (131 072 at 128x128, B = 128)
 // the prologue (barrier init, TMEM allocation, first TMA round trip) of one overlaps the math of the other.
-template <int DH, bool SHORT>
-__global__ void __launch_bounds__(kThreads, SHORT ? 2 : 1)
+// DUAL (long key sequences) = the same economy for the flash loop: S, P and O single-buffered (256 TMEM columns),
+// a two-stage K/V ring, 112 KB of shared memory - again two CTAs per SM.  Inside one CTA the chain
+// S_j -> softmax_j -> PV_j is then serial (the next S is issued as soon as the softmax warps have consumed the
+// current one), and the overlap the double buffers gave comes from the OTHER resident CTA instead - which also
+// doubles the softmax warps per scheduler, the actual limiter of the one-CTA arrangement (one warp per
+// scheduler cannot hide its tcgen05.ld / MUFU latencies) and hides the per-CTA prologue and epilogue.
+template <int DH, bool SHORT, bool DUAL>
+__global__ void __launch_bounds__(kThreads, (SHORT || DUAL) ? 2 : 1)
 fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                     const __grid_constant__ CUtensorMap mapV, const AttnDev p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  constexpr int NKV = SHORT ? 1 : kKV;               // K/V ring stages
-  constexpr int NPB = SHORT ? 1 : 2;                 // P tiles
-  constexpr uint32_t O_COL = SHORT ? 128u : 256u;    // first TMEM column of the O accumulator(s)
-  constexpr uint32_t TMEM_COLS = SHORT ? 256u : 512u;
+  static_assert(!(SHORT && DUAL), "SHORT has no loop to single-buffer");
+  extern __shared__ __align__(1024) uint8_t smem_fwd_raw[];
+  uint8_t* const smem_raw = smem_fwd_raw;
+  uint8_t* smem;
+  if constexpr (DUAL) {
+    // no alignment slack in the request (2 x 113 KB + the per-CTA reserve must fit the SM): the dynamic window
+    // has to start 1024-byte aligned by itself - fail loudly if it ever does not
+    smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  } else {
+    smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  }
+  constexpr bool ONE = SHORT || DUAL;                // single S / P / O buffers
+  constexpr int NKV = SHORT ? 1 : (DUAL ? 2 : kKV);  // K/V ring stages
+  constexpr int NPB = ONE ? 1 : 2;                   // P tiles
+  constexpr uint32_t O_COL = ONE ? 128u : 256u;      // first TMEM column of the O accumulator(s)
+  constexpr uint32_t TMEM_COLS = ONE ? 256u : 512u;
+  auto sb = [](int j) { return ONE ? 0 : (j & 1); };                 // S / P / O buffer of block j
+  auto sph = [](int j) { return ONE ? (j & 1) : ((j >> 1) & 1); };   // ... and the parity of its barrier phase
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + kTile;                       // NKV x (K tile, V tile)
   uint8_t* sP = sKV + NKV * 2 * kTile;               // NPB x (two 64-key chunks)
@@ -144,26 +162,28 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         const uint32_t aK = smem_u32(sKV + s * 2 * kTile) + koff;
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          umma_f16(tmem_base + (uint32_t)((j & 1) * 128), umma_desc_sw128(aQ + k * 32, 16, 1024),
+          umma_f16(tmem_base + (uint32_t)(sb(j) * 128), umma_desc_sw128(aQ + k * 32, 16, 1024),
                    umma_desc_sw128(aK + k * 32, 16, 1024), idS, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
+        umma_commit(&s_full[sb(j)]);
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
       issue_s(0);
       for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) issue_s(j + 1);
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        if (!ONE && j + 1 < nblk) issue_s(j + 1);
+        mbar_wait(&p_full[sb(j)], sph(j));
         tc_fence_after();
+        // single S buffer: the softmax warps have consumed S_j (they publish P_j after their last tcgen05.ld)
+        if (ONE && j + 1 < nblk) issue_s(j + 1);
         const int s = j % NKV;
         const uint32_t aP = smem_u32(sP + (j % NPB) * 2 * kTile);
         const uint32_t aV = smem_u32(sKV + s * 2 * kTile + kTile) + koff;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_f16(tmem_base + O_COL + (uint32_t)((j & 1) * 64),
+          umma_f16(tmem_base + O_COL + (uint32_t)(sb(j) * 64),
                    umma_desc_sw128(aP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
                    umma_desc_sw128(aV + k * 2048, 8192, 1024), idO, k != 0 ? 1u : 0u);
-        umma_commit(&o_full[j & 1]);
+        umma_commit(&o_full[sb(j)]);
         umma_commit(&kv_empty[s]);
       }
     }
@@ -177,12 +197,12 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     for (int i = 0; i < DH; ++i) acc[i] = 0.f;
 
     auto fold_o = [&](int j, float corr) {      // acc = acc * corr + O_j
-      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&o_full[sb(j)], sph(j));
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < DH; c += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(lane_addr + O_COL + (uint32_t)((j & 1) * 64 + c), v);
+        tmem_ld_32x32(lane_addr + O_COL + (uint32_t)(sb(j) * 64 + c), v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], corr, __uint_as_float(v[i]));
@@ -190,9 +210,9 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     };
 
     for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[sb(j)], sph(j));
       tc_fence_after();
-      const uint32_t sa = lane_addr + (uint32_t)((j & 1) * 128);
+      const uint32_t sa = lane_addr + (uint32_t)(sb(j) * 128);
       const int kbase = j * 128;
       // pass A: row maximum over the valid keys
       float mx = -INFINITY;
@@ -207,6 +227,9 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       }
       const float m_new = fmaxf(m, mx * p.scale_log2);
       const float corr = ex2(m - m_new);           // first block: exp2(-inf) = 0
+      // single P / O buffers: PV_{j-1} must have retired before P_j overwrites its operand, and O_{j-1} must be
+      // read before PV_j overwrites it - fold it in here, between the two passes
+      if (ONE && j > 0) fold_o(j - 1, corr_prev);
       // pass B: probabilities -> bf16 -> the swizzled A tile of the PV MMA
       float rs = 0.f;
       const uint32_t sPj = smem_u32(sP + (j % NPB) * 2 * kTile);
@@ -229,8 +252,8 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
-      if (j > 0) fold_o(j - 1, corr_prev);
+      if (lane == 0) mbar_arrive(&p_full[sb(j)]);
+      if (!ONE && j > 0) fold_o(j - 1, corr_prev);
       corr_prev = corr;
     }
     fold_o(nblk - 1, corr_prev);
@@ -291,8 +314,13 @@ __global__ void attn_dvec_kernel(const AttnDev p) {
 // Shared memory: R1, R2 = the two row-side operands (Q, dO | K, V), ring of (C1, C2) = the column-side pair
 // (K_j, V_j | Q_i, dO_i), E1 / E2 tiles of 2 x 16 KB each.
 // ======================================================================================================
-template <int DH, bool ROWS_ARE_KEYS>
-__global__ void __launch_bounds__(kThreads, 1)
+// EWG = number of 4-warp groups that turn S / dP into the E tiles.  The element-wise step (two tcgen05.ld, exp2,
+// two bf16 packs and swizzled stores per element) is what bounds the kernel - 128 columns per thread with one
+// warp per scheduler cannot hide its own latencies - and it has no cross-column dependency (the softmax
+// statistics are inputs), so with EWG = 2 the warps (2..5) take columns 0..63 of every row and (6..9) columns
+// 64..127: two warps per scheduler on the same TMEM lanes.
+template <int DH, bool ROWS_ARE_KEYS, int EWG>
+__global__ void __launch_bounds__(64 + 128 * EWG, 1)
 fdx_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_constant__ CUtensorMap mapR2,
                     const __grid_constant__ CUtensorMap mapC1, const __grid_constant__ CUtensorMap mapC2,
                     const AttnDev p) {
@@ -330,7 +358,7 @@ fdx_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_cons
     mbar_init(r_full, 1);
     for (int i = 0; i < RING; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(e_full, 4);
+    mbar_init(e_full, 4 * EWG);
     mbar_init(e_free, 1);
     mbar_init(done, 1);
     fence_barrier_init();
@@ -402,6 +430,8 @@ fdx_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_cons
     }
   } else {
     const int q = warp & 3;
+    const int wg = (warp - 2) >> 2;                    // element-wise warp group: columns [wg * 128 / EWG, ...)
+    constexpr int CW = 128 / EWG;                      // columns per thread and step
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const long long stat_base = ((long long)b * p.heads + head) * p.L;
@@ -418,39 +448,47 @@ fdx_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_cons
       const int cbase = j * 128;
       if constexpr (ROWS_ARE_KEYS) {
         // stage the query-side statistics of this step (parity buffer j & 1), 128 threads = 128 columns
-        float* st = sStat + (j & 1) * 256;
-        const bool ok = cbase + row < p.L;
-        st[row] = ok ? p.lse[stat_base + cbase + row] * kLog2e : 0.f;
-        st[128 + row] = ok ? p.dvec[stat_base + cbase + row] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (wg == 0) {
+          float* st = sStat + (j & 1) * 256;
+          const bool ok = cbase + row < p.L;
+          st[row] = ok ? p.lse[stat_base + cbase + row] * kLog2e : 0.f;
+          st[128 + row] = ok ? p.dvec[stat_base + cbase + row] : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * EWG) : "memory");
       }
       if (j > 0) mbar_wait(e_free, (j - 1) & 1);      // previous step's accumulation has consumed E1 / E2
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const float* st = sStat + (j & 1) * 256;
+      const bool row_in = ROWS_ARE_KEYS ? (r0 + row < p.Lk) : (r0 + row < p.L);
+      const int col_lim = (ROWS_ARE_KEYS ? p.L : p.Lk) - cbase;      // columns of this step inside the tensor
 #pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
+      for (int c = wg * CW; c < (wg + 1) * CW; c += 32) {
         uint32_t vs[32], vp[32], w1[16], w2[16];
         tmem_ld_32x32(lane_addr + (uint32_t)c, vs);
         tmem_ld_32x32(lane_addr + 128u + (uint32_t)c, vp);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pr[2], ds[2];
+        for (int i = 0; i < 32; i += 4) {
+          float lq[4] = {lse_r, lse_r, lse_r, lse_r}, dq4[4] = {d_r, d_r, d_r, d_r};
+          if constexpr (ROWS_ARE_KEYS) {
+            const float4 a4 = *reinterpret_cast<const float4*>(st + c + i);
+            const float4 b4 = *reinterpret_cast<const float4*>(st + 128 + c + i);
+            lq[0] = a4.x; lq[1] = a4.y; lq[2] = a4.z; lq[3] = a4.w;
+            dq4[0] = b4.x; dq4[1] = b4.y; dq4[2] = b4.z; dq4[3] = b4.w;
+          }
+          float pr[4], ds[4];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int col = cbase + c + i + u;
-            const int kidx = ROWS_ARE_KEYS ? (r0 + row) : col;       // key index of this element
-            const int qidx = ROWS_ARE_KEYS ? col : (r0 + row);       // query index
-            const float lse_q = ROWS_ARE_KEYS ? st[c + i + u] : lse_r;
-            const float d_q = ROWS_ARE_KEYS ? st[128 + c + i + u] : d_r;
-            const bool ok = (kidx < p.Lk) && (qidx < p.L);
-            const float pv = ok ? ex2(fmaf(__uint_as_float(vs[i + u]), p.scale_log2, -lse_q)) : 0.f;
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = row_in && (c + i + u < col_lim);
+            const float pv = ok ? ex2(fmaf(__uint_as_float(vs[i + u]), p.scale_log2, -lq[u])) : 0.f;
             pr[u] = pv;
-            ds[u] = pv * (__uint_as_float(vp[i + u]) - d_q) * p.scale;
+            ds[u] = pv * (__uint_as_float(vp[i + u]) - dq4[u]) * p.scale;
           }
           w1[i >> 1] = pack_bf16x2(pr[0], pr[1]);
+          w1[(i >> 1) + 1] = pack_bf16x2(pr[2], pr[3]);
           w2[i >> 1] = pack_bf16x2(ds[0], ds[1]);
+          w2[(i >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
         }
         if constexpr (ROWS_ARE_KEYS) store_p_chunk(sE1a, row, c, w1);
         store_p_chunk(sE2a, row, c, w2);
@@ -477,6 +515,7 @@ fdx_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_cons
       base += head * DH;
 #pragma unroll
       for (int c = 0; c < DH; c += 32) {
+        if (EWG == 2 && ((which * (DH / 32) + c / 32) & 1) != wg) continue;   // the 32-column pieces alternate
         uint32_t v[32];
         tmem_ld_32x32(lane_addr + 256u + (uint32_t)(which * 64 + c), v);
         tmem_ld_wait();
@@ -536,22 +575,29 @@ int fdx_attention_fwd(const fdx_attn_desc* a, void* stream) {
   d.o = (__nv_bfloat16*)a->o; d.o_ld = a->o_ld; d.o_bs = a->o_bs;
   d.lse = a->lse;
   const bool short_keys = a->Lk <= 128 && !getenv("FDX_ATTN_NO_SHORT");
-  const int smem = (short_keys ? (1 + 2 + 2) : (1 + 2 * kKV + 4)) * kTile + 1024 + 256;
+  const bool dual = !short_keys && !getenv("FDX_ATTN_NO_DUAL");      // two CTAs per SM for the flash loop
+  const int smem = short_keys ? (1 + 2 + 2) * kTile + 1024 + 256
+                   : dual     ? (1 + 2 * 2 + 2) * kTile + 256
+                              : (1 + 2 * kKV + 4) * kTile + 1024 + 256;
   dim3 grid((a->L + 127) / 128, a->heads, a->B);
-  static bool attr[4] = {false, false, false, false};
-#define FDX_ATTN_FWD_LAUNCH(DHV, SH, IDX)                                                                      \
-  {                                                                                                            \
-    if (!attr[IDX]) {                                                                                          \
-      FDX_CUDA(cudaFuncSetAttribute(fdx_attn_fwd_kernel<DHV, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                    smem));                                                                    \
-      attr[IDX] = true;                                                                                        \
-    }                                                                                                          \
-    fdx_attn_fwd_kernel<DHV, SH><<<grid, kThreads, smem, (cudaStream_t)stream>>>(mQ, mK, mV, d);                \
+  static bool attr[6] = {false, false, false, false, false, false};
+#define FDX_ATTN_FWD_LAUNCH(DHV, SH, DU, IDX)                                                                     \
+  {                                                                                                               \
+    if (!attr[IDX]) {                                                                                             \
+      FDX_CUDA(cudaFuncSetAttribute(fdx_attn_fwd_kernel<DHV, SH, DU>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    smem));                                                                       \
+      attr[IDX] = true;                                                                                           \
+    }                                                                                                             \
+    fdx_attn_fwd_kernel<DHV, SH, DU><<<grid, kThreads, smem, (cudaStream_t)stream>>>(mQ, mK, mV, d);               \
   }
   if (a->dh == 64) {
-    if (short_keys) FDX_ATTN_FWD_LAUNCH(64, true, 0) else FDX_ATTN_FWD_LAUNCH(64, false, 1)
+    if (short_keys) FDX_ATTN_FWD_LAUNCH(64, true, false, 0)
+    else if (dual) FDX_ATTN_FWD_LAUNCH(64, false, true, 4)
+    else FDX_ATTN_FWD_LAUNCH(64, false, false, 1)
   } else {
-    if (short_keys) FDX_ATTN_FWD_LAUNCH(32, true, 2) else FDX_ATTN_FWD_LAUNCH(32, false, 3)
+    if (short_keys) FDX_ATTN_FWD_LAUNCH(32, true, false, 2)
+    else if (dual) FDX_ATTN_FWD_LAUNCH(32, false, true, 5)
+    else FDX_ATTN_FWD_LAUNCH(32, false, false, 3)
   }
 #undef FDX_ATTN_FWD_LAUNCH
   fdx_note_kernel(FDX_KERNEL_ATTN_FWD);
@@ -585,19 +631,23 @@ int fdx_attention_bwd(const fdx_attn_desc* a, void* stream) {
     FDX_LAUNCH_CHECK();
   }
   const int smem = (2 + 2 * 2 + 4) * kTile + 2 * 256 * 4 + 1024 + 256;
-  static bool attr[4] = {false, false, false, false};
-#define FDX_ATTN_BWD_LAUNCH(DHV, RK, IDX, GRIDX, M1, M2, M3, M4)                                                  \
+  static bool attr[8] = {false, false, false, false, false, false, false, false};
+  const bool one_group = getenv("FDX_ATTN_BWD_EWG1") != nullptr;   // round-2a arrangement: four element-wise warps
+#define FDX_ATTN_BWD_LAUNCH1(DHV, RK, EW, IDX, GRIDX, M1, M2, M3, M4)                                             \
   {                                                                                                                \
     if (!attr[IDX]) {                                                                                              \
-      FDX_CUDA(cudaFuncSetAttribute(fdx_attn_bwd_kernel<DHV, RK>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+      FDX_CUDA(cudaFuncSetAttribute(fdx_attn_bwd_kernel<DHV, RK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     smem));                                                                        \
       attr[IDX] = true;                                                                                            \
     }                                                                                                              \
     dim3 grid((GRIDX + 127) / 128, a->heads, a->B);                                                                \
-    fdx_attn_bwd_kernel<DHV, RK><<<grid, kThreads, smem, st>>>(M1, M2, M3, M4, d);                                 \
+    fdx_attn_bwd_kernel<DHV, RK, EW><<<grid, 64 + 128 * EW, smem, st>>>(M1, M2, M3, M4, d);                        \
     fdx_note_kernel(FDX_KERNEL_ATTN_BWD);                                                                          \
     FDX_LAUNCH_CHECK();                                                                                            \
   }
+#define FDX_ATTN_BWD_LAUNCH(DHV, RK, IDX, GRIDX, M1, M2, M3, M4)                                                  \
+  if (one_group) FDX_ATTN_BWD_LAUNCH1(DHV, RK, 1, IDX, GRIDX, M1, M2, M3, M4)                                      \
+  else FDX_ATTN_BWD_LAUNCH1(DHV, RK, 2, (IDX + 4), GRIDX, M1, M2, M3, M4)
   if (a->dh == 64) {
     FDX_ATTN_BWD_LAUNCH(64, false, 0, a->L, mQ, mDO, mK, mV)      // dQ: rows = queries (Q, dO), loop (K_j, V_j)
     FDX_ATTN_BWD_LAUNCH(64, true, 1, a->Lk, mK, mV, mQ, mDO)      // dK/dV: rows = keys (K, V), loop (Q_i, dO_i)
@@ -606,6 +656,7 @@ int fdx_attention_bwd(const fdx_attn_desc* a, void* stream) {
     FDX_ATTN_BWD_LAUNCH(32, true, 3, a->Lk, mK, mV, mQ, mDO)
   }
 #undef FDX_ATTN_BWD_LAUNCH
+#undef FDX_ATTN_BWD_LAUNCH1
   return FDX_OK;
 }
 

@@ -162,19 +162,29 @@ __device__ __forceinline__ f32x2_t gn_dz_pair(f32x2_t x, f32x2_t dy, f32x2_t ah,
   return f2_mul(dy, f2_mul(s, u));
 }
 
+// red != nullptr: the finalize step is MERGED into this kernel - both of its outputs are linear in the
+// per-(image, channel) sums, so every CTA adds its partial's contribution straight into red[n][g][2] (zeroed by
+// the caller), dgamma[c] and dbeta[c], and zeroes the column-sum outputs the second pass accumulates into.
+// One launch (and one dependent-launch gap) less on the backward's critical path per GroupNorm.
 template <bool SILU>
 __global__ void __launch_bounds__(kNT, 3)
 gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                     const __nv_bfloat16* __restrict__ dy, long long dps, int HW, int C, int G,
                     const float* __restrict__ stats, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, float eps, float* __restrict__ ws) {
+                    const float* __restrict__ beta, float eps, float* __restrict__ ws,
+                    float* __restrict__ red, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    float* __restrict__ csum_img, float* __restrict__ csum_tot) {
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  extern __shared__ float shm[];   // 2 * [rows*C]
+  extern __shared__ float shm[];   // 2 * [rows*C] (+ 2 * C with the merged finalize)
   float* part0 = shm;
   float* part1 = part0 + rows * C;
   const float cnt = (float)HW * (float)cpg;
+  if (red && blockIdx.x == 0) {
+    if (csum_img) for (int c = tid; c < C; c += kNT) csum_img[(long long)n * C + c] = 0.f;
+    if (csum_tot && n == 0) for (int c = tid; c < C; c += kNT) csum_tot[c] = 0.f;
+  }
   if (tid < rows * vpp) {
     const int cv = tid % vpp, r = tid / vpp;
     const int g = (cv * 8) / cpg;
@@ -229,6 +239,31 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
     }
   }
   __syncthreads();
+  if (red) {
+    float* gr0 = part1 + rows * C;   // [C] gamma_c * S0,  [C] gamma_c * rstd * (S1 - mean * S0)
+    float* gr1 = gr0 + C;
+    for (int c = tid; c < C; c += kNT) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int rr = 0; rr < rows; ++rr) { t0 += part0[rr * C + c]; t1 += part1[rr * C + c]; }
+      const int g = c / cpg;
+      const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
+      const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+      const float u = rsqrtf(var + eps) * (t1 - mean * t0);
+      atomicAdd(&dbeta[c], t0);
+      atomicAdd(&dgamma[c], u);
+      const float ga = gamma[c];
+      gr0[c] = ga * t0;
+      gr1[c] = ga * u;
+    }
+    __syncthreads();
+    for (int g = tid; g < G; g += kNT) {
+      float r0 = 0.f, r1 = 0.f;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { r0 += gr0[c]; r1 += gr1[c]; }
+      atomicAdd(&red[(long long)n * 2 * G + 2 * g], r0);
+      atomicAdd(&red[(long long)n * 2 * G + 2 * g + 1], r1);
+    }
+    return;
+  }
   // per-(image, channel) partial sums: only gridDim.x (<= ~10) atomics ever hit one address
   for (int c = tid; c < C; c += kNT) {
     float t0 = 0.f, t1 = 0.f;
@@ -385,7 +420,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                     const float* __restrict__ stats, const float* __restrict__ red,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                     __nv_bfloat16* __restrict__ dx, long long dxps, float* __restrict__ csum_img,
-                    const __nv_bfloat16* __restrict__ acc, long long accps) {
+                    const __nv_bfloat16* __restrict__ acc, long long accps, float* __restrict__ csum_tot) {
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
@@ -468,6 +503,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
       float v = 0.f;
       for (int rr = 0; rr < rows; ++rr) v += sh_cs[rr * C + c];
       atomicAdd(&csum_img[(long long)n * C + c], v);
+      if (csum_tot) atomicAdd(&csum_tot[c], v);     // zeroed by the first pass (merged finalize)
     }
   }
 }
@@ -1091,7 +1127,7 @@ dim3 gn_grid(const fdx_act* x, int unroll, int resident) {
 // second pass of the GroupNorm backward: template dispatch on (activation, accumulate, column sums)
 void launch_bwd_apply(const fdx_act* x, const fdx_act* dy, int groups, const float* stats, const float* red,
                       const float* gamma, const float* beta, float eps, int silu, const fdx_act* dx,
-                      const fdx_act* acc, float* csum_img, cudaStream_t st) {
+                      const fdx_act* acc, float* csum_img, cudaStream_t st, float* csum_tot = nullptr) {
   const int accumulate = acc != nullptr;
   const int C = x->c, HW = x->h * x->w;
   const size_t shm = csum_img ? sizeof(float) * (kNT / (C / 8)) * C : 0;
@@ -1104,7 +1140,7 @@ void launch_bwd_apply(const fdx_act* x, const fdx_act* dy, int groups, const flo
                                                          groups, stats, red, gamma, beta, eps, op,       \
                                                          dx->pix_stride, csum_img,                                 \
                                                          (const __nv_bfloat16*)(acc ? acc->ptr : nullptr),          \
-                                                         (long long)(acc ? acc->pix_stride : 0))
+                                                         (long long)(acc ? acc->pix_stride : 0), csum_tot)
   const int key = (silu ? 4 : 0) | (accumulate ? 2 : 0) | (csum_img ? 1 : 0);
   switch (key) {
     case 0: FDX_GN_APPLY(false, false, false); break;
@@ -1258,17 +1294,30 @@ static int groupnorm_bwd_impl(const fdx_act* x, const fdx_act* dy, int groups, c
     }
     return FDX_OK;
   }
-  FDX_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, st));
-  const size_t shm = sizeof(float) * 2 * (kNT / (C / 8)) * C;
+  // FDX_GN_FINALIZE=1: the round-1 sequence (sums workspace, finalize launch, reduce_rows launch)
+  static const bool separate_finalize = [] {
+    const char* e = getenv("FDX_GN_FINALIZE");
+    return e && e[0] && e[0] != '0';
+  }();
+  const bool merged = !separate_finalize;
+  if (merged) FDX_CUDA(cudaMemsetAsync(red, 0, sizeof(float) * 2 * N * groups, st));
+  else FDX_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, st));
+  const size_t shm = sizeof(float) * (2 * (size_t)(kNT / (C / 8)) * C + (merged ? 2 * C : 0));
+  float* red_arg = merged ? red : nullptr;
   if (silu)
     gn_bwd_stats_kernel<true><<<gn_grid(x, kBU, 3), kNT, shm, st>>>(
         (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, HW, C,
-        groups, stats, gamma, beta, eps, sums);
+        groups, stats, gamma, beta, eps, sums, red_arg, dgamma, dbeta, csum_img, csum_tot);
   else
     gn_bwd_stats_kernel<false><<<gn_grid(x, kBU, 3), kNT, shm, st>>>(
         (const __nv_bfloat16*)x->ptr, x->pix_stride, (const __nv_bfloat16*)dy->ptr, dy->pix_stride, HW, C,
-        groups, stats, gamma, beta, eps, sums);
+        groups, stats, gamma, beta, eps, sums, red_arg, dgamma, dbeta, csum_img, csum_tot);
   FDX_LAUNCH_CHECK();
+  if (merged) {
+    launch_bwd_apply(x, dy, groups, stats, red, gamma, beta, eps, silu, dx, acc, csum_img, st, csum_tot);
+    FDX_LAUNCH_CHECK();
+    return FDX_OK;
+  }
   const int cb = (C + kFinC - 1) / kFinC, gb = (N * groups + 7) / 8;
   gn_bwd_finalize_kernel<<<cb + gb, 256, 0, st>>>(sums, stats, gamma, N, HW, C, groups, eps, cb, red, dgamma,
                                                    dbeta);

@@ -346,7 +346,16 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         valid = (x < p.W) && (y < p.H) && (n < p.N);
         img = n;
         obase = (long long)n * p.os_n + (long long)y * p.os_y + (long long)x * p.os_x;
-        if (p.res) rbase = (long long)n * p.rs_n + (long long)y * p.rs_y + (long long)x * p.rs_x;
+        if (p.res) {
+          rbase = (long long)n * p.rs_n + (long long)y * p.rs_y + (long long)x * p.rs_x;
+          // the side input of this row: request all of its lines now (L2 prefetch), before the accumulator
+          // wait - the epilogue's own register prefetch runs only one 64-column chunk ahead
+          if (valid && !p.out_f32 && !p.out_atomic) {
+            const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(p.res) + rbase + nt * BN;
+            const int ncol = min(BN, p.Ncols - nt * BN);
+            for (int c = 0; c < ncol; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + c));
+          }
+        }
       } else {
         const MnTile mt_ = decode_mn(p, tile);
         nt = mt_.nt;
@@ -628,7 +637,12 @@ int fdx_tc_launch(const TcLaunch& L, cudaStream_t stream) {
     if (r3 != FDX_ERR_UNSUPPORTED) return r3;
   }
   if (L.mode != TC_MNMN) {
-    while (BN > 64 && pix_blocks * ((L.Ncols + BN - 1) / BN) < 2LL * fdx_num_sms())
+    // Round 1 narrowed the column tile until the launch had two waves of tiles.  But a K = 16 MMA of this
+    // (pixels-as-M) engine costs ~150 cycles whatever its N, so a tile's duration does not shrink
+    // with BN and more, narrower tiles only add rounds: 8x8 images (128 pixel tiles at B = 256) ran 256 -> 256 at
+    // BN = 64 in four rounds instead of one (47 us; 407 TF/s).  FDX_TC_BN_V1=1 restores the old rule.
+    static const bool bn_v1 = getenv("FDX_TC_BN_V1") != nullptr;
+    while (bn_v1 && BN > 64 && pix_blocks * ((L.Ncols + BN - 1) / BN) < 2LL * fdx_num_sms())
       BN = (BN == 192) ? 64 : BN / 2;
     d.nblks = (L.Ncols + BN - 1) / BN;
     d.kchunks = (L.K + kBK - 1) / kBK;

@@ -149,10 +149,12 @@ def test_groupnorm_backward_fused_into_dgrad(B, H, W, cin, cout):
     assert rel(outs[0][0], xr.grad) < 2e-2 and rel(outs[0][1], gr.grad) < 2e-2 and rel(outs[0][2], br.grad) < 2e-2
 
 
-@pytest.mark.parametrize("env_kv", [{"FDX_GN_2PASS": "0"}, {"FDX_GN_2PASS": "0", "FDX_GN_PIPE": "2"}])
+@pytest.mark.parametrize("env_kv", [{"FDX_GN_2PASS": "0"}, {"FDX_GN_2PASS": "0", "FDX_GN_PIPE": "2"},
+                                    {"FDX_GN_FINALIZE": "1"}])
 def test_groupnorm_backward_single_launch_variants(env_kv):
-    """The cluster / pipelined GroupNorm-backward kernels are selected once per process: run the GroupNorm
-    parity tests (all shapes, silu on/off, accumulate, column sums) in a child process with the switch set."""
+    """The cluster / pipelined GroupNorm-backward kernels and the round-1 separate-finalize sequence are selected
+    once per process: run the GroupNorm parity tests (all shapes, silu on/off, accumulate, column sums) in a
+    child process with the switch set."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
