@@ -24,7 +24,8 @@
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                 // two groups of four: the tile's pixel columns are split between them
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kPixBytes = 2 * 128 * 128;     // two boxes of 128 pixels x 64 channels bf16
 
 struct TctDev {
@@ -55,7 +56,7 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   constexpr int kWBytes = MT * 128;                       // MT channels x 64 k
   constexpr int kHaloBytes = 18 * 16 * 128;               // 16 x 18 pixel box
   constexpr int kStageBytes = HALO ? (3 * kWBytes + kHaloBytes) : (kWBytes + kPixBytes);
-  constexpr int S = HALO ? ((MT == 128) ? 2 : 3) : ((MT == 128) ? 4 : 5);
+  constexpr int S = HALO ? ((MT == 128) ? 2 : 3) : ((MT == 128) ? 3 : 4);
   constexpr bool IL = (MT == 64);                         // two interleaved pixel halves per tile
   constexpr int NH = IL ? 2 : 1;
   constexpr int TH = 16 * NH;                             // pixel rows per tile
@@ -75,7 +76,7 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     tma_prefetch_desc(&mapX);
     for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
+    mbar_init(&tempty[0], kEpiWarps); mbar_init(&tempty[1], kEpiWarps);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -202,14 +203,20 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     // (CW = channels per warp: 32 at M=128, 16 at M=64) and leave as 16-byte channel pieces: lane ->
     // (pixel l / PPX + k * (32 / PPX), piece l % PPX).  A lane always owns the same 8 channels, so the
     // fused GroupNorm sums are per-lane registers, reduced once per tile.
+    // Eight epilogue warps (round 2): the 64- and 128-channel layers were EPILOGUE bound (64 -> 64 at 64x64:
+    // 110 us against 67 us of MMA time; per 32-pixel chunk one tcgen05.ld -> staging -> 16-byte pieces chain per
+    // warp with nothing to overlap it).  Warps 2..5 take the pixel columns 0..127 of the accumulator, warps 6..9
+    // the columns 128..255 - same TMEM lanes (warp % 4), own staging tile, own GroupNorm partial sums.
     const int q = warp & 3;
+    const int ew = warp - 2;                             // 0 .. kEpiWarps-1: staging tile of this warp
+    const int c_begin = (ew >> 2) * (256 / (kEpiWarps / 4)), c_end = c_begin + 256 / (kEpiWarps / 4);
     constexpr int CW = 32;                               // staging slots per pixel column = lanes of the warp:
                                                          // M=128: 32 channels; M=64: 16 channels x 2 halves
     constexpr int PPX = 4;                               // 16-byte pieces per staged pixel column
     constexpr int CPW = IL ? 16 : 32;                    // channels owned by one warp
     const int crow = IL ? q * 16 + (lane & 15) : q * 32 + lane;
     constexpr int RS = CW + 4;                           // padded row (floats): conflict-free 16-byte reads
-    float* stg = reinterpret_cast<float*>(smem + S * kStageBytes + 256) + q * (32 * RS);   // [32 px][RS] f32
+    float* stg = reinterpret_cast<float*>(smem + S * kStageBytes + 256) + ew * (32 * RS);  // [32 px][RS] f32
     const int piece = lane % PPX, prow = lane / PPX;     // read phase: this lane's piece and first pixel
     int acc = 0; uint32_t acc_phase = 0;
     __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(p.out);
@@ -225,7 +232,7 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       const int xb_ = mt_ % p.nxb, yb_ = (mt_ / p.nxb) % p.nyb, nb_ = mt_ / (p.nxb * p.nyb);
       const int nch = min(MT, p.Ncols - cb_ * MT);
       const __nv_bfloat16* base = resp + (long long)nb_ * p.rs_n + (long long)(xb_ * 16) * p.rs_x + cb_ * MT;
-      for (int pi = q * 32 + lane; pi < TH * 16; pi += 128) {
+      for (int pi = ew * 32 + lane; pi < TH * 16; pi += 32 * kEpiWarps) {
         const int y = yb_ * TH + (pi >> 4);
         if (y >= p.H) continue;
         const __nv_bfloat16* a = base + (long long)y * p.rs_y + (long long)(pi & 15) * p.rs_x;
@@ -258,13 +265,13 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         for (int k = 0; k < PPX; ++k) {
           const int j = prow + k * (32 / PPX);
           r[k] = make_uint4(0, 0, 0, 0);
-          if (resp && ch_ok && c0 < 256)
+          if (resp && ch_ok && c0 < c_end)
             r[k] = *reinterpret_cast<const uint4*>(resp + rbase + (long long)(c0 / 16 + (j >> 4)) * p.rs_y +
                                                    (long long)(j & 15) * p.rs_x + ch);
         }
       };
       uint4 rcur[PPX], rnxt[PPX];
-      load_res(0, rcur);
+      load_res(c_begin, rcur);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
@@ -272,7 +279,7 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
 #pragma unroll 1
-      for (int c0 = 0; c0 < 256; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(t_addr + c0, v);
         tmem_ld_wait();
@@ -343,9 +350,10 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 
 template <int MT, bool A_MN, bool HALO>
 int launch_tct(const CUtensorMap& mW, const CUtensorMap& mX, const TctDev& d, cudaStream_t stream) {
-  constexpr int S = HALO ? ((MT == 128) ? 2 : 3) : ((MT == 128) ? 4 : 5);
+  constexpr int S = HALO ? ((MT == 128) ? 2 : 3) : ((MT == 128) ? 3 : 4);
   constexpr int stage = HALO ? (3 * MT * 128 + 18 * 16 * 128) : (MT * 128 + kPixBytes);
-  constexpr int smem = S * stage + 1024 + 256 + 20480 /* epilogue transpose tiles */;
+  constexpr int smem = S * stage + 1024 + 256 + kEpiWarps * 32 * 36 * 4 /* epilogue transpose tiles */;
+  static_assert(smem <= 227 * 1024, "tct: shared memory");
   static bool attr_set = false;
   if (!attr_set) {
     FDX_CUDA(cudaFuncSetAttribute(fdx_tct_kernel<MT, A_MN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
