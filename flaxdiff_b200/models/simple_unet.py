@@ -51,6 +51,11 @@ def _attn_width(d: int) -> int:
     return 32 if d <= 32 else 64
 
 
+# 1x1 residual convolutions (ResidualBlock.residual_conv): conv-geometry launches by default - since the transposed
+# engine got eight epilogue warps they beat the flat GEMM launch on the HBM-bound shapes
+# (profiles/layers_r02_res1x1.txt); FDX_RES1X1_GEMM=1 restores the flat launch.
+_RES1X1_GEMM = bool(os.environ.get("FDX_RES1X1_GEMM"))
+
 class _SideStream:
     """Weight-gradient kernels have no consumer before the optimizer step, so the backward pass issues them
     on a second stream: the HBM-bound GroupNorm-backward kernels of the main (data-gradient) chain then
@@ -527,8 +532,11 @@ class Unet:
         if cin != cout:
             Bn, hh, ww, _ = x.shape
             r = torch.empty((Bn, hh, ww, cout), dtype=BF16, device=x.device)
-            ops.gemm(GEMM_KMN, x, W16[f"{name}/residual_conv/conv/kernel"], r, Bn * hh * ww, cout, cin,
-                     x.stride(2), cout, cout, bias=W[f"{name}/residual_conv/conv/bias"])
+            if _RES1X1_GEMM:      # round-1 launch: one flat GEMM over all pixels (pixels-as-M engine)
+                ops.gemm(GEMM_KMN, x, W16[f"{name}/residual_conv/conv/kernel"], r, Bn * hh * ww, cout, cin,
+                         x.stride(2), cout, cout, bias=W[f"{name}/residual_conv/conv/bias"])
+            else:                 # conv geometry: eligible for the transposed engine (8 epilogue warps)
+                ops.conv1x1_fwd(x, W16[f"{name}/residual_conv/conv/kernel"], W[f"{name}/residual_conv/conv/bias"], out=r)
         else:
             r = x
         ops.conv3x3_fwd(a2, W16[f"{name}/conv2/conv/kernel"], W[f"{name}/conv2/conv/bias"], res=r, out=dst.t,
@@ -1024,8 +1032,11 @@ class Unet:
             else:
                 ops.act_add(dx, dout, dx)
         elif cin != cout:
-            ops.gemm(GEMM_KK, dout, W16[kres + "kernel"].view(cin, cout), dx, M, cin, cout, dout.stride(2), cout,
-                     dx.stride(2), res=dx if acc else None, r_ld=dx.stride(2) if acc else 0)
+            if _RES1X1_GEMM:
+                ops.gemm(GEMM_KK, dout, W16[kres + "kernel"].view(cin, cout), dx, M, cin, cout, dout.stride(2), cout,
+                         dx.stride(2), res=dx if acc else None, r_ld=dx.stride(2) if acc else 0)
+            else:
+                ops.conv1x1_dgrad(dout, W16[kres + "kernel"], dx, accumulate=acc)
             ops.conv_dgrad_groupnorm_bwd(*gn1, True)
         elif acc:
             ops.conv_dgrad_groupnorm_bwd(*gn1, True)
