@@ -25,6 +25,7 @@
 #include "fdx_common.cuh"
 #include "../../include/fdx.h"
 #include <math.h>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace {
@@ -214,16 +215,27 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       tc_fence_after();
       const uint32_t sa = lane_addr + (uint32_t)(sb(j) * 128);
       const int kbase = j * 128;
-      // pass A: row maximum over the valid keys
+      // pass A: row maximum over the valid keys (only the last key block can be partial)
+      const bool partial = kbase + 128 > p.Lk;
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(sa + c, v);
         tmem_ld_wait();
+        if (partial) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + c + i < p.Lk) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c + i < p.Lk) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+          float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};        // four independent chains
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m4[u], __uint_as_float(v[i + u]));
+          }
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        }
       }
       const float m_new = fmaxf(m, mx * p.scale_log2);
       const float corr = ex2(m - m_new);           // first block: exp2(-inf) = 0
@@ -238,13 +250,20 @@ fdx_attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         uint32_t v[32], w[16];
         tmem_ld_32x32(sa + c, v);
         tmem_ld_wait();
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (kbase + c + i < p.Lk) ? ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new)) : 0.f;
-          float p1 = (kbase + c + i + 1 < p.Lk) ? ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new)) : 0.f;
-          rs += p0 + p1;
-          w[i >> 1] = pack_bf16x2(p0, p1);
+        for (int i = 0; i < 32; i += 4) {
+          float pe[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            pe[u] = ex2(fmaf(__uint_as_float(v[i + u]), p.scale_log2, -m_new));
+            if (partial && !(kbase + c + i + u < p.Lk)) pe[u] = 0.f;
+            rs4[u] += pe[u];
+          }
+          w[i >> 1] = pack_bf16x2(pe[0], pe[1]);
+          w[(i >> 1) + 1] = pack_bf16x2(pe[2], pe[3]);
         }
+        rs += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
         store_p_chunk(sPj, row, c, w);
       }
       l = fmaf(l, corr, rs);
@@ -440,7 +459,7 @@ fdx_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_cons
     if constexpr (!ROWS_ARE_KEYS) {
       if (r0 + row < p.L) {
         lse_r = p.lse[stat_base + r0 + row] * kLog2e;
-        d_r = p.dvec[stat_base + r0 + row];
+        d_r = p.dvec[stat_base + r0 + row] * p.scale;
       }
     }
     const uint32_t sE1a = smem_u32(sE1), sE2a = smem_u32(sE2);
@@ -452,7 +471,7 @@ fdx_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_cons
           float* st = sStat + (j & 1) * 256;
           const bool ok = cbase + row < p.L;
           st[row] = ok ? p.lse[stat_base + cbase + row] * kLog2e : 0.f;
-          st[128 + row] = ok ? p.dvec[stat_base + cbase + row] : 0.f;
+          st[128 + row] = ok ? p.dvec[stat_base + cbase + row] * p.scale : 0.f;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(128 * EWG) : "memory");
       }
@@ -462,37 +481,45 @@ fdx_attn_bwd_kernel(const __grid_constant__ CUtensorMap mapR1, const __grid_cons
       const float* st = sStat + (j & 1) * 256;
       const bool row_in = ROWS_ARE_KEYS ? (r0 + row < p.Lk) : (r0 + row < p.L);
       const int col_lim = (ROWS_ARE_KEYS ? p.L : p.Lk) - cbase;      // columns of this step inside the tensor
+      // P = exp2(s * scale*log2e - lse*log2e);  dS = P * (dP * scale - D * scale)  (D * scale staged / hoisted).
+      // Only the last step / the last row tile needs the bounds masks: MASK = false is the 5-instruction path.
+      auto ewise = [&](auto mask_tag) {
+        constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll 1
-      for (int c = wg * CW; c < (wg + 1) * CW; c += 32) {
-        uint32_t vs[32], vp[32], w1[16], w2[16];
-        tmem_ld_32x32(lane_addr + (uint32_t)c, vs);
-        tmem_ld_32x32(lane_addr + 128u + (uint32_t)c, vp);
-        tmem_ld_wait();
+        for (int c = wg * CW; c < (wg + 1) * CW; c += 32) {
+          uint32_t vs[32], vp[32], w1[16], w2[16];
+          tmem_ld_32x32(lane_addr + (uint32_t)c, vs);
+          tmem_ld_32x32(lane_addr + 128u + (uint32_t)c, vp);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float lq[4] = {lse_r, lse_r, lse_r, lse_r}, dq4[4] = {d_r, d_r, d_r, d_r};
-          if constexpr (ROWS_ARE_KEYS) {
-            const float4 a4 = *reinterpret_cast<const float4*>(st + c + i);
-            const float4 b4 = *reinterpret_cast<const float4*>(st + 128 + c + i);
-            lq[0] = a4.x; lq[1] = a4.y; lq[2] = a4.z; lq[3] = a4.w;
-            dq4[0] = b4.x; dq4[1] = b4.y; dq4[2] = b4.z; dq4[3] = b4.w;
-          }
-          float pr[4], ds[4];
+          for (int i = 0; i < 32; i += 4) {
+            float lq[4] = {lse_r, lse_r, lse_r, lse_r}, dq4[4] = {d_r, d_r, d_r, d_r};
+            if constexpr (ROWS_ARE_KEYS) {
+              const float4 a4 = *reinterpret_cast<const float4*>(st + c + i);
+              const float4 b4 = *reinterpret_cast<const float4*>(st + 128 + c + i);
+              lq[0] = a4.x; lq[1] = a4.y; lq[2] = a4.z; lq[3] = a4.w;
+              dq4[0] = b4.x; dq4[1] = b4.y; dq4[2] = b4.z; dq4[3] = b4.w;
+            }
+            float pr[4], ds[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const bool ok = row_in && (c + i + u < col_lim);
-            const float pv = ok ? ex2(fmaf(__uint_as_float(vs[i + u]), p.scale_log2, -lq[u])) : 0.f;
-            pr[u] = pv;
-            ds[u] = pv * (__uint_as_float(vp[i + u]) - dq4[u]) * p.scale;
+            for (int u = 0; u < 4; ++u) {
+              float pv = ex2(fmaf(__uint_as_float(vs[i + u]), p.scale_log2, -lq[u]));
+              if (MASK && !(row_in && (c + i + u < col_lim))) pv = 0.f;
+              pr[u] = pv;
+              ds[u] = pv * fmaf(__uint_as_float(vp[i + u]), p.scale, -dq4[u]);
+            }
+            w1[i >> 1] = pack_bf16x2(pr[0], pr[1]);
+            w1[(i >> 1) + 1] = pack_bf16x2(pr[2], pr[3]);
+            w2[i >> 1] = pack_bf16x2(ds[0], ds[1]);
+            w2[(i >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
           }
-          w1[i >> 1] = pack_bf16x2(pr[0], pr[1]);
-          w1[(i >> 1) + 1] = pack_bf16x2(pr[2], pr[3]);
-          w2[i >> 1] = pack_bf16x2(ds[0], ds[1]);
-          w2[(i >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
+          if constexpr (ROWS_ARE_KEYS) store_p_chunk(sE1a, row, c, w1);
+          store_p_chunk(sE2a, row, c, w2);
         }
-        if constexpr (ROWS_ARE_KEYS) store_p_chunk(sE1a, row, c, w1);
-        store_p_chunk(sE2a, row, c, w2);
-      }
+      };
+      // warp-uniform choice (the TMEM loads inside are warp-collective)
+      const bool need_mask = __any_sync(0xffffffffu, !row_in) || col_lim < 128;
+      if (need_mask) ewise(std::true_type{}); else ewise(std::false_type{});
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
