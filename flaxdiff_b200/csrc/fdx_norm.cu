@@ -420,11 +420,45 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
                     const float* __restrict__ stats, const float* __restrict__ red,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                     __nv_bfloat16* __restrict__ dx, long long dxps, float* __restrict__ csum_img,
-                    const __nv_bfloat16* __restrict__ acc, long long accps, float* __restrict__ csum_tot) {
+                    const __nv_bfloat16* __restrict__ acc, long long accps, float* __restrict__ csum_tot,
+                    const float* __restrict__ slot_ws, int slots, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta) {
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  extern __shared__ float sh_cs[];   // [rows*C] when column sums are requested
+  extern __shared__ float sh_cs[];   // [rows*C] when column sums are requested (+ [2C + 2G] with slot_ws)
+  // slot_ws != nullptr (fused first pass: the data-gradient epilogue left S0 = sum dz, S1 = sum dz*x per slot):
+  // every CTA derives its image's per-group constants itself - no collapse / finalize launches - and the
+  // first CTA of each image adds the image's share of dgamma / dbeta.
+  float* pro = sh_cs + (CS ? rows * C : 0);
+  if (slot_ws) {
+    const float cnt_ = (float)HW * (float)cpg;
+    const int N = gridDim.y;
+    for (int c = tid; c < C; c += kNT) {
+      float S0 = 0.f, S1 = 0.f;
+      for (int sl = 0; sl < slots; ++sl) {
+        const float* b = slot_ws + (((long long)sl * N + n) * 2) * C;
+        S0 += b[c];
+        S1 += b[C + c];
+      }
+      const int g = c / cpg;
+      const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt_;
+      const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt_ - mean * mean);
+      const float u = rsqrtf(var + eps) * (S1 - mean * S0);
+      if (blockIdx.x == 0) { atomicAdd(&dbeta[c], S0); atomicAdd(&dgamma[c], u); }
+      const float ga = gamma[c];
+      pro[c] = ga * S0;
+      pro[C + c] = ga * u;
+    }
+    __syncthreads();
+    for (int g = tid; g < G; g += kNT) {
+      float r0 = 0.f, r1 = 0.f;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { r0 += pro[c]; r1 += pro[C + c]; }
+      pro[2 * C + 2 * g] = r0;
+      pro[2 * C + 2 * g + 1] = r1;
+    }
+    __syncthreads();
+  }
   if (tid < rows * vpp) {
     const int cv = tid % vpp, r = tid / vpp;
     const int g = (cv * 8) / cpg;
@@ -432,8 +466,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps,
     const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
     const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
     const float rstd = rsqrtf(var + eps);
-    const float m1 = red[(long long)n * 2 * G + 2 * g] / cnt;
-    const float m2 = red[(long long)n * 2 * G + 2 * g + 1] / cnt;
+    const float m1 = (slot_ws ? pro[2 * C + 2 * g] : red[(long long)n * 2 * G + 2 * g]) / cnt;
+    const float m2 = (slot_ws ? pro[2 * C + 2 * g + 1] : red[(long long)n * 2 * G + 2 * g + 1]) / cnt;
     const float c2 = rstd * rstd * m2;
     const float c3 = mean * c2 - rstd * m1;
     const f32x2_t nc2 = f2_pack(-c2, -c2), c3p = f2_pack(c3, c3);
@@ -1127,10 +1161,12 @@ dim3 gn_grid(const fdx_act* x, int unroll, int resident) {
 // second pass of the GroupNorm backward: template dispatch on (activation, accumulate, column sums)
 void launch_bwd_apply(const fdx_act* x, const fdx_act* dy, int groups, const float* stats, const float* red,
                       const float* gamma, const float* beta, float eps, int silu, const fdx_act* dx,
-                      const fdx_act* acc, float* csum_img, cudaStream_t st, float* csum_tot = nullptr) {
+                      const fdx_act* acc, float* csum_img, cudaStream_t st, float* csum_tot = nullptr,
+                      const float* slot_ws = nullptr, int slots = 0, float* dgamma = nullptr, float* dbeta = nullptr) {
   const int accumulate = acc != nullptr;
   const int C = x->c, HW = x->h * x->w;
-  const size_t shm = csum_img ? sizeof(float) * (kNT / (C / 8)) * C : 0;
+  const size_t shm = (csum_img ? sizeof(float) * (kNT / (C / 8)) * C : 0) +
+                     (slot_ws ? sizeof(float) * (2 * (size_t)C + 2 * groups) : 0);
   const dim3 grid = gn_grid(x, kBU, accumulate ? 2 : 3);
   const __nv_bfloat16* xp = (const __nv_bfloat16*)x->ptr;
   const __nv_bfloat16* dp = (const __nv_bfloat16*)dy->ptr;
@@ -1140,7 +1176,8 @@ void launch_bwd_apply(const fdx_act* x, const fdx_act* dy, int groups, const flo
                                                          groups, stats, red, gamma, beta, eps, op,       \
                                                          dx->pix_stride, csum_img,                                 \
                                                          (const __nv_bfloat16*)(acc ? acc->ptr : nullptr),          \
-                                                         (long long)(acc ? acc->pix_stride : 0), csum_tot)
+                                                         (long long)(acc ? acc->pix_stride : 0), csum_tot, slot_ws, \
+                                                         slots, dgamma, dbeta)
   const int key = (silu ? 4 : 0) | (accumulate ? 2 : 0) | (csum_img ? 1 : 0);
   switch (key) {
     case 0: FDX_GN_APPLY(false, false, false); break;
@@ -1362,10 +1399,10 @@ int fdx_groupnorm_coeffs(const float* stats, const float* gamma, const float* be
   return FDX_OK;
 }
 
-int fdx_groupnorm_bwd_dz(const fdx_act* x, const fdx_act* dz, int groups, const float* stats,
-                         const float* gamma, float eps, const float* ws_slots, int slots, float* ws,
-                         float* dgamma, float* dbeta, const fdx_act* dx, int accumulate, float* csum_img,
-                         float* csum_tot, void* stream) {
+static int groupnorm_bwd_dz_impl(const fdx_act* x, const fdx_act* dz, int groups, const float* stats,
+                                 const float* gamma, float eps, const float* ws_slots, int slots, float* ws,
+                                 float* dgamma, float* dbeta, const fdx_act* dx, const fdx_act* acc,
+                                 float* csum_img, float* csum_tot, void* stream) {
   int s = gn_check(x, groups, "groupnorm_bwd_dz");
   if (s != FDX_OK) return s;
   FDX_REQUIRE(dz && dz->ptr && dx && dx->ptr && ws && ws_slots && slots > 0 && dgamma && dbeta,
@@ -1376,6 +1413,19 @@ int fdx_groupnorm_bwd_dz(const fdx_act* x, const fdx_act* dz, int groups, const 
   FDX_REQUIRE(!csum_tot || csum_img, "groupnorm_bwd_dz: csum_tot needs csum_img");
   cudaStream_t st = (cudaStream_t)stream;
   const int N = x->n, C = x->c, HW = x->h * x->w;
+  static const bool separate_finalize = [] {
+    const char* e = getenv("FDX_GN_FINALIZE");
+    return e && e[0] && e[0] != '0';
+  }();
+  if (!separate_finalize) {
+    // one launch: the apply kernel's prologue collapses the slots and derives the per-group constants
+    if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * N * C, st));
+    if (csum_tot) FDX_CUDA(cudaMemsetAsync(csum_tot, 0, sizeof(float) * C, st));
+    launch_bwd_apply(x, dz, groups, stats, nullptr, gamma, gamma, eps, 0, dx, acc, csum_img, st, csum_tot, ws_slots,
+                     slots, dgamma, dbeta);
+    FDX_LAUNCH_CHECK();
+    return FDX_OK;
+  }
   float* sums = ws;                         // [N][C][2]
   float* red = ws + 2LL * N * C;            // [N][G][2]
   long long cg = ((long long)N * C + 255) / 256;
@@ -1388,13 +1438,32 @@ int fdx_groupnorm_bwd_dz(const fdx_act* x, const fdx_act* dz, int groups, const 
   FDX_LAUNCH_CHECK();
   if (csum_img) FDX_CUDA(cudaMemsetAsync(csum_img, 0, sizeof(float) * N * C, st));
   // dz already carries silu'(z): the second pass is the activation-free one (beta is not read)
-  launch_bwd_apply(x, dz, groups, stats, red, gamma, gamma, eps, 0, dx, accumulate ? dx : nullptr, csum_img, st);
+  launch_bwd_apply(x, dz, groups, stats, red, gamma, gamma, eps, 0, dx, acc, csum_img, st);
   FDX_LAUNCH_CHECK();
   if (csum_tot) {
     reduce_rows_kernel<<<(C + 31) / 32, 256, 0, st>>>(csum_img, N, C, csum_tot, 0);
     FDX_LAUNCH_CHECK();
   }
   return FDX_OK;
+}
+
+int fdx_groupnorm_bwd_dz(const fdx_act* x, const fdx_act* dz, int groups, const float* stats,
+                         const float* gamma, float eps, const float* ws_slots, int slots, float* ws,
+                         float* dgamma, float* dbeta, const fdx_act* dx, int accumulate, float* csum_img,
+                         float* csum_tot, void* stream) {
+  return groupnorm_bwd_dz_impl(x, dz, groups, stats, gamma, eps, ws_slots, slots, ws, dgamma, dbeta, dx,
+                               accumulate ? dx : nullptr, csum_img, csum_tot, stream);
+}
+
+int fdx_groupnorm_bwd_dz_add(const fdx_act* x, const fdx_act* dz, int groups, const float* stats,
+                             const float* gamma, float eps, const float* ws_slots, int slots, float* ws,
+                             float* dgamma, float* dbeta, const fdx_act* dx, const fdx_act* addend,
+                             float* csum_img, float* csum_tot, void* stream) {
+  FDX_REQUIRE(addend && addend->ptr, "groupnorm_bwd_dz_add: null addend");
+  FDX_REQUIRE(addend->c == x->c && addend->n == x->n && addend->h == x->h && addend->w == x->w,
+              "groupnorm_bwd_dz_add: addend shape mismatch");
+  return groupnorm_bwd_dz_impl(x, dz, groups, stats, gamma, eps, ws_slots, slots, ws, dgamma, dbeta, dx, addend,
+                               csum_img, csum_tot, stream);
 }
 
 int fdx_rmsnorm_fwd(const fdx_act* x, const float* scale, float eps, const fdx_act* y,

@@ -20,6 +20,7 @@
 // Same barrier topology as fdx_tc.cu: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue,
 // double-buffered 2 x 256-column TMEM accumulator.  Geometry: stride 1, W and H multiples of 16.
 #include "fdx_tc.cuh"
+#include "fdx_epilogue.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -41,6 +42,7 @@ struct TctDev {
   long long rs_x, rs_y, rs_n;
   float* cs_ws;            // fused per-(image, channel) sums or null
   int cs_slots, cs_ld;
+  const float* gn_ab;      // GNB kernels: [N][2][Ncols] GroupNorm coefficients a, b of the tensor `res` (= x)
 };
 
 // HALO = true (round 2, 3x3 stride-1 only): the 64- and 128-output-channel layers were L2 -> shared-memory
@@ -49,7 +51,12 @@ struct TctDev {
 // 16 x 18 pixels (rows y0-1 .. y0+16) is loaded per (kx, K chunk); the three ky taps are 2048-byte row offsets
 // into it (swizzle-aligned views, exactly as in the nine-tap weight gradient), so a stage carries three weight
 // tiles + 36 KB of pixels and feeds twelve MMAs: 96 -> 36 KB of pixel traffic per three taps.
-template <int MT, bool A_MN, bool HALO>
+// GNB = true (data gradient only): the first pass of the GroupNorm(+SiLU) backward in the epilogue - with x = the
+// GroupNorm input (side input `res`) and z = a_c x + b_c the kernel stores dz = dy * silu'(z) instead of dy and
+// accumulates S0 = sum dz, S1 = sum dz * x per (image, channel) into the column-sum workspace, exactly as the
+// pixels-as-M engine's EPI_GN_BWD (fdx_epilogue.cuh).  There the silu' arithmetic sat in four epilogue warps and
+// lost to the separate statistics pass; with eight epilogue warps it fits under the tile's MMA time.
+template <int MT, bool A_MN, bool HALO, bool GNB>
 __global__ void __launch_bounds__(kThreads, 1)
 fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
                const TctDev p) {
@@ -260,6 +267,18 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       // residual pieces are requested one 32-pixel chunk ahead (the first before the accumulator wait)
       const int ch = cw0 + (IL ? (piece & 1) : piece) * 8;   // read phase: this lane's first channel
       const bool ch_ok = ch < p.Ncols && yh < p.H;           // (H % 32 == 16: the last tile has no half 1)
+      float ga[8], gb[8];
+      if constexpr (GNB) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ga[i] = 0.f; gb[i] = 0.f; }
+        if (ch_ok) {
+          const float4* a4 = reinterpret_cast<const float4*>(p.gn_ab + (long long)nb * 2 * p.Ncols + ch);
+          const float4* b4 = reinterpret_cast<const float4*>(p.gn_ab + ((long long)nb * 2 + 1) * p.Ncols + ch);
+          const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+          ga[0] = a0.x; ga[1] = a0.y; ga[2] = a0.z; ga[3] = a0.w; ga[4] = a1.x; ga[5] = a1.y; ga[6] = a1.z; ga[7] = a1.w;
+          gb[0] = b0.x; gb[1] = b0.y; gb[2] = b0.z; gb[3] = b0.w; gb[4] = b1.x; gb[5] = b1.y; gb[6] = b1.z; gb[7] = b1.w;
+        }
+      }
       auto load_res = [&](int c0, uint4 (&r)[PPX]) {
 #pragma unroll
         for (int k = 0; k < PPX; ++k) {
@@ -297,12 +316,20 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           const float4 b = *reinterpret_cast<const float4*>(stg + j * RS + piece * 8 + 4);
           float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
           if (ch_ok) {
+            float xv[8];
             if (resp) {
               const uint4 r = rcur[k];
               const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z),
                            r3 = unpack_bf16x2(r.w);
-              f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
-              f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+              xv[0] = r0.x; xv[1] = r0.y; xv[2] = r1.x; xv[3] = r1.y;
+              xv[4] = r2.x; xv[5] = r2.y; xv[6] = r3.x; xv[7] = r3.y;
+              if constexpr (GNB) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = epi_silu_grad_times(f[i], fmaf(xv[i], ga[i], gb[i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += xv[i];
+              }
             }
             uint4 o;
             o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
@@ -312,8 +339,9 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
               const float2 h0 = unpack_bf16x2(o.x), h1 = unpack_bf16x2(o.y), h2 = unpack_bf16x2(o.z),
                            h3 = unpack_bf16x2(o.w);
               const float hv[8] = {h0.x, h0.y, h1.x, h1.y, h2.x, h2.y, h3.x, h3.y};
+              // second factor: the GroupNorm input x (GNB) or the stored value itself (forward column statistics)
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { s0[i] += hv[i]; s1[i] = fmaf(hv[i], hv[i], s1[i]); }
+              for (int i = 0; i < 8; ++i) { s0[i] += hv[i]; s1[i] = fmaf(hv[i], GNB ? xv[i] : hv[i], s1[i]); }
             }
           }
         }
@@ -348,7 +376,7 @@ fdx_tct_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-template <int MT, bool A_MN, bool HALO>
+template <int MT, bool A_MN, bool HALO, bool GNB = false>
 int launch_tct(const CUtensorMap& mW, const CUtensorMap& mX, const TctDev& d, cudaStream_t stream) {
   constexpr int S = HALO ? ((MT == 128) ? 2 : 3) : ((MT == 128) ? 3 : 4);
   constexpr int stage = HALO ? (3 * MT * 128 + 18 * 16 * 128) : (MT * 128 + kPixBytes);
@@ -356,13 +384,13 @@ int launch_tct(const CUtensorMap& mW, const CUtensorMap& mX, const TctDev& d, cu
   static_assert(smem <= 227 * 1024, "tct: shared memory");
   static bool attr_set = false;
   if (!attr_set) {
-    FDX_CUDA(cudaFuncSetAttribute(fdx_tct_kernel<MT, A_MN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FDX_CUDA(cudaFuncSetAttribute(fdx_tct_kernel<MT, A_MN, HALO, GNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   int grid = fdx_num_sms();
   if (grid <= 0) return FDX_ERR_NO_DEVICE;
   if (d.ntiles < grid) grid = d.ntiles;
-  fdx_tct_kernel<MT, A_MN, HALO><<<grid, kThreads, smem, stream>>>(mW, mX, d);
+  fdx_tct_kernel<MT, A_MN, HALO, GNB><<<grid, kThreads, smem, stream>>>(mW, mX, d);
   fdx_note_kernel(FDX_KERNEL_TCT);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
@@ -372,8 +400,10 @@ int launch_tct(const CUtensorMap& mW, const CUtensorMap& mX, const TctDev& d, cu
 
 // FDX_ERR_UNSUPPORTED (no error text) = geometry not covered; the caller uses the generic engine.
 int fdx_tct_launch(const TcLaunch& L, cudaStream_t stream) {
-  if (L.mode == TC_MNMN || L.gemm_like || L.es != 1 || L.out_f32 || L.out_atomic || L.gn_ab || L.b_batched)
+  if (L.mode == TC_MNMN || L.gemm_like || L.es != 1 || L.out_f32 || L.out_atomic || L.b_batched)
     return FDX_ERR_UNSUPPORTED;
+  // fused GroupNorm-backward first pass: data gradient with x as the side input and the sums workspace
+  if (L.gn_ab && (L.mode != TC_KK || !L.res || !L.gn_ws || L.bias || L.rowvec)) return FDX_ERR_UNSUPPORTED;
   // column counts the generic engine would have to cover with N < 256 tiles (64, 128, 192, 320, 384, ...)
   if (L.Ncols % 64 != 0 || L.Ncols % 256 == 0 || L.Ncols > 512) return FDX_ERR_UNSUPPORTED;
   if (L.W % 16 != 0 || L.H % 16 != 0 || L.K % 64 != 0) return FDX_ERR_UNSUPPORTED;
@@ -390,6 +420,7 @@ int fdx_tct_launch(const TcLaunch& L, cudaStream_t stream) {
   d.alpha = L.alpha; d.bias = L.bias; d.rowvec = L.rowvec;
   d.res = L.res; d.rs_x = L.rs_x; d.rs_y = L.rs_y; d.rs_n = L.rs_n;
   d.cs_ws = L.gn_ws; d.cs_slots = L.gn_slots > 0 ? L.gn_slots : 1; d.cs_ld = L.ws_ld > 0 ? L.ws_ld : L.Ncols;
+  d.gn_ab = L.gn_ab;
 
   // halo-sharing variant: standard 3x3 stride-1 tap set in (ky, kx) order.  FDX_TCT_HALO=0 disables it,
   // FDX_TCT_HALO=64 / 128 restricts it to that M tile.
@@ -420,6 +451,12 @@ int fdx_tct_launch(const TcLaunch& L, cudaStream_t stream) {
 #define FDX_TCT_GO(M_, AMN_)                                                                   \
   (halo ? launch_tct<M_, AMN_, true>(mW, mX, d, stream) : launch_tct<M_, AMN_, false>(mW, mX, d, stream))
   if (L.mode == TC_KMN) return MT == 128 ? FDX_TCT_GO(128, true) : FDX_TCT_GO(64, true);
+  if (L.gn_ab) {
+#define FDX_TCT_GN(M_) \
+  (halo ? launch_tct<M_, false, true, true>(mW, mX, d, stream) : launch_tct<M_, false, false, true>(mW, mX, d, stream))
+    return MT == 128 ? FDX_TCT_GN(128) : FDX_TCT_GN(64);
+#undef FDX_TCT_GN
+  }
   return MT == 128 ? FDX_TCT_GO(128, false) : FDX_TCT_GO(64, false);
 #undef FDX_TCT_GO
 }

@@ -217,8 +217,17 @@ def conv3x3_dgrad_gn(dy: torch.Tensor, w_hwio: torch.Tensor, dz: torch.Tensor, x
 
 
 def groupnorm_bwd_dz(x, dz, groups, stats, gamma, eps, ws_slots, dgamma, dbeta, dx,
-                     accumulate: bool = False, csum_img=None, csum_tot=None) -> torch.Tensor:
+                     accumulate: bool = False, csum_img=None, csum_tot=None, addend=None) -> torch.Tensor:
     red = torch.empty(2 * x.shape[0] * (x.shape[-1] + groups), dtype=torch.float32, device=x.device)
+    if addend is not None:
+        assert not accumulate, "groupnorm_bwd_dz: addend and accumulate are exclusive"
+        check(load().fdx_groupnorm_bwd_dz_add(ctypes.byref(act(x, "x")), ctypes.byref(act(dz, "dz")),
+                                              ctypes.c_int(groups), ptr(stats), ptr(gamma), ctypes.c_float(eps),
+                                              ptr(ws_slots), ctypes.c_int(ws_slots.shape[0]), ptr(red), ptr(dgamma),
+                                              ptr(dbeta), ctypes.byref(act(dx, "dx")),
+                                              ctypes.byref(act(addend, "addend")), ptr(csum_img), ptr(csum_tot),
+                                              stream_ptr()), "groupnorm_bwd_dz_add")
+        return dx
     check(load().fdx_groupnorm_bwd_dz(ctypes.byref(act(x, "x")), ctypes.byref(act(dz, "dz")),
                                       ctypes.c_int(groups), ptr(stats), ptr(gamma), ctypes.c_float(eps),
                                       ptr(ws_slots), ctypes.c_int(ws_slots.shape[0]), ptr(red), ptr(dgamma),
@@ -228,21 +237,34 @@ def groupnorm_bwd_dz(x, dz, groups, stats, gamma, eps, ws_slots, dgamma, dbeta, 
     return dx
 
 
+def _gn_fuse_default(x: torch.Tensor, dy: torch.Tensor) -> bool:
+    """The fused first pass is the default where the data gradient runs on the transposed engine (eight epilogue
+    warps hide the silu' arithmetic): Cin = 64 ... 512 not a multiple of 256, 16-aligned images."""
+    cin, h, w = x.shape[-1], x.shape[1], x.shape[2]
+    return (cin % 64 == 0 and cin % 256 != 0 and cin <= 512 and dy.shape[-1] % 64 == 0 and h % 16 == 0 and
+            w % 16 == 0 and h * w >= GN_FUSE_MIN_PIXELS)
+
+
 def conv_dgrad_groupnorm_bwd(dy, w_hwio, x, groups, stats, gamma, beta, eps, dgamma, dbeta, dx,
                              accumulate: bool = False, csum_img=None, csum_tot=None,
                              fused: Optional[bool] = None, addend=None) -> torch.Tensor:
-    """d/dx of conv3x3(silu(groupnorm(x))) given dy = d/d(conv output): data gradient, then the two-pass
-    GroupNorm backward.  FDX_GN_FUSE=1 selects the fused dgrad epilogue instead (parity-tested, but
-    measured slower on B200 except when Cout >= 2 Cin: one epilogue warp per scheduler cannot hide the
-    latency of the silu' arithmetic - profiles/layers_r01_gn_fusion.txt)."""
+    """d/dx of conv3x3(silu(groupnorm(x))) given dy = d/d(conv output): the data gradient with the first pass
+    of the GroupNorm backward in its epilogue (dz = dy * silu'(z), sum dz, sum dz*x) where that convolution runs
+    on the transposed engine, then ONE pass over x and dz; elsewhere data gradient + the two-pass GroupNorm
+    backward.  FDX_GN_FUSE=0: never fused; FDX_GN_FUSE=1: fused wherever an image has >= 128 pixels (also on the
+    pixels-as-M engine, where four epilogue warps make it slower - profiles/layers_r01_gn_fusion.txt)."""
     da = torch.empty(tuple(x.shape), dtype=torch.bfloat16, device=x.device)
     if fused is None:
-        fused = bool(os.environ.get("FDX_GN_FUSE"))
-    if fused and addend is None and x.shape[1] * x.shape[2] >= GN_FUSE_MIN_PIXELS:
+        env = os.environ.get("FDX_GN_FUSE")
+        if env is None or env == "":
+            fused = _gn_fuse_default(x, dy)
+        else:
+            fused = env != "0" and x.shape[1] * x.shape[2] >= GN_FUSE_MIN_PIXELS
+    if fused and x.shape[1] * x.shape[2] >= GN_FUSE_MIN_PIXELS:
         ab = groupnorm_coeffs(stats, gamma, beta, x.shape[1] * x.shape[2], eps)
         ws = conv3x3_dgrad_gn(dy, w_hwio, da, x, ab)
         return groupnorm_bwd_dz(x, da, groups, stats, gamma, eps, ws, dgamma, dbeta, dx, accumulate,
-                                csum_img=csum_img, csum_tot=csum_tot)
+                                csum_img=csum_img, csum_tot=csum_tot, addend=addend)
     conv3x3_dgrad(dy, w_hwio, da)
     return groupnorm_bwd(x, da, groups, stats, gamma, beta, eps, True, dgamma, dbeta, dx, accumulate,
                          csum_img=csum_img, csum_tot=csum_tot, addend=addend)

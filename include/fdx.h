@@ -162,6 +162,12 @@ int fdx_groupnorm_bwd_dz(const fdx_act* x, const fdx_act* dz, int groups, const 
                          const float* gamma, float eps, const float* ws_slots, int slots, float* ws,
                          float* dgamma, float* dbeta, const fdx_act* dx, int accumulate, float* csum_img,
                          float* csum_tot, void* stream);
+/* fdx_groupnorm_bwd_dz with dx = GroupNorm backward + addend (the identity-residual gradient of the
+ * ResidualBlock, flaxdiff/models/common.py:334-336), as fdx_groupnorm_bwd_add. */
+int fdx_groupnorm_bwd_dz_add(const fdx_act* x, const fdx_act* dz, int groups, const float* stats,
+                             const float* gamma, float eps, const float* ws_slots, int slots, float* ws,
+                             float* dgamma, float* dbeta, const fdx_act* dx, const fdx_act* addend,
+                             float* csum_img, float* csum_tot, void* stream);
 /* nn.RMSNorm(eps) over channels (models/attention.py:325-326). C a multiple of 8, <= 1024. */
 int fdx_rmsnorm_fwd(const fdx_act* x, const float* scale, float eps, const fdx_act* y,
                     void* stream);

@@ -96,6 +96,13 @@ def test_conv_dgrad_groupnorm_bwd_fused(shape, fused):
     dg.zero_(); db.zero_()
     ops.conv_dgrad_groupnorm_bwd(dy, w16, x, 8, st, gamma, beta, 1e-4, dg, db, dx2, accumulate=True, fused=fused)
     assert rel(dx2, xr.grad + base.float().cpu()) < 1.2e-2
+    # the identity-residual gradient as an addend of the second pass (fdx_groupnorm_bwd_add / _bwd_dz_add)
+    add = torch.randn(B, H, W, C, device=dev).bfloat16()
+    dx3 = torch.empty_like(dx)
+    dg.zero_(); db.zero_()
+    ops.conv_dgrad_groupnorm_bwd(dy, w16, x, 8, st, gamma, beta, 1e-4, dg, db, dx3, fused=fused, addend=add)
+    assert rel(dx3, xr.grad + add.float().cpu()) < 1.2e-2
+    assert rel(dg, gr.grad) < 8e-3 and rel(db, br.grad) < 8e-3
 
 
 @pytest.mark.parametrize("C", [256, 512])
