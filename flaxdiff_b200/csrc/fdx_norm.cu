@@ -1243,7 +1243,7 @@ static int groupnorm_bwd_impl(const fdx_act* x, const fdx_act* dy, int groups, c
   const int accumulate = acc != nullptr;
   int s = gn_check(x, groups, "groupnorm_bwd");
   if (s != FDX_OK) return s;
-  FDX_REQUIRE(dy && dy->ptr && dx && dx->ptr && ws, "groupnorm_bwd: null tensor");
+  FDX_REQUIRE(dy && dy->ptr && dx && dx->ptr && ws && dgamma && dbeta, "groupnorm_bwd: null tensor");
   FDX_REQUIRE(dy->c == x->c && dx->c == x->c && dy->n == x->n && dx->n == x->n &&
                   dy->h == x->h && dy->w == x->w && dx->h == x->h && dx->w == x->w,
               "groupnorm_bwd: shape mismatch");
