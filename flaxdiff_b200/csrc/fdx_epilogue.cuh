@@ -230,6 +230,11 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
         s0[i] += __shfl_xor_sync(0xffffffffu, s0[i], 16);
         s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], 16);
       }
+      // Each warp adds its own 32-row partial (lanes 0..7 own 8 channels each) with 16-byte reductions.  Round 1
+      // exchanged the four warps' partials through shared memory behind a 128-thread barrier per 64-column
+      // chunk - that barrier serialised the epilogue warps (Upsample forward: 15 K cycles per 128 x 256 tile against
+      // 4.8 K of MMA time).  FDX_EPI_XCHG (compile-time) keeps the old exchange for comparison.
+#ifdef FDX_EPI_XCHG
       float* xb = xchg + (*par) * 512 + q * 128;      // [par][warp][which][64]
       if (lane < 8) {
 #pragma unroll
@@ -255,6 +260,20 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
                        : "memory");
         }
       }
+#else
+      if (lane < 8 && (piece < 4 || half2)) {
+        float* d0 = e.gn_ws + (((long long)slot * e.gn_N + img0) * 2) * e.ws_ld + col0 + piece * 8;
+        float* d1 = d0 + e.ws_ld;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d0), "f"(s0[0]), "f"(s0[1]), "f"(s0[2]),
+                     "f"(s0[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d0 + 4), "f"(s0[4]), "f"(s0[5]),
+                     "f"(s0[6]), "f"(s0[7]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d1), "f"(s1[0]), "f"(s1[1]), "f"(s1[2]),
+                     "f"(s1[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d1 + 4), "f"(s1[4]), "f"(s1[5]),
+                     "f"(s1[6]), "f"(s1[7]) : "memory");
+      }
+#endif
       *par ^= 1;
     }
     __syncwarp();
