@@ -233,7 +233,34 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
       // Each warp adds its own 32-row partial (lanes 0..7 own 8 channels each) with 16-byte reductions.  Round 1
       // exchanged the four warps' partials through shared memory behind a 128-thread barrier per 64-column
       // chunk - that barrier serialised the epilogue warps (Upsample forward: 15 K cycles per 128 x 256 tile against
-      // 4.8 K of MMA time).
+      // 4.8 K of MMA time).  FDX_EPI_XCHG (compile-time) keeps the old exchange for comparison.
+#ifdef FDX_EPI_XCHG
+      float* xb = xchg + (*par) * 512 + q * 128;      // [par][warp][which][64]
+      if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xb[piece * 8 + i] = s0[i];
+          xb[64 + piece * 8 + i] = s1[i];
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps
+      if (q == 0) {
+        const int which = lane >> 4, c4 = (lane & 15) * 4;
+        const float* xs = xchg + (*par) * 512 + which * 64 + c4;
+        float4 t = *reinterpret_cast<const float4*>(xs);
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          const float4 o = *reinterpret_cast<const float4*>(xs + w * 128);
+          t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        }
+        if (c4 < 32 || half2) {
+          float* dst = e.gn_ws + (((long long)slot * e.gn_N + img0) * 2 + which) * e.ws_ld + col0 + c4;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y),
+                       "f"(t.z), "f"(t.w)
+                       : "memory");
+        }
+      }
+#else
       if (lane < 8 && (piece < 4 || half2)) {
         float* d0 = e.gn_ws + (((long long)slot * e.gn_N + img0) * 2) * e.ws_ld + col0 + piece * 8;
         float* d1 = d0 + e.ws_ld;
@@ -246,6 +273,7 @@ __device__ __forceinline__ void epilogue_bf16_coalesced(const EpiArgs& e, uint8_
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d1 + 4), "f"(s1[4]), "f"(s1[5]),
                      "f"(s1[6]), "f"(s1[7]) : "memory");
       }
+#endif
       *par ^= 1;
     }
     __syncwarp();

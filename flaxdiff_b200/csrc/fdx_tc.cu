@@ -22,8 +22,7 @@
 
 namespace {
 
-constexpr int kThreads = 192;            // CTA-pair kernels: producer + issuer + four epilogue warps
-constexpr int kThreads2 = 320;           // everything else: TWO groups of four epilogue warps (see the epilogue)
+constexpr int kThreads = 192;
 constexpr int kBK = 64;                 // K elements (or K rows) per pipeline stage
 constexpr int kABytes = 128 * kBK * 2;  // 16 KB per stage for A in every mode
 
@@ -38,8 +37,8 @@ struct TcCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kSub * (kABytes + kBBytes);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
-                                    32768 /*epilogue staging: 8 warps x 4 KB*/;
-  static_assert(kSmemBytes <= 227 * 1024, "tc: shared memory");
+                                    16384 /*epilogue staging: 4 warps x 4 KB*/ +
+                                    4096 /*GroupNorm-backward column-sum exchange*/;
   // Every M=128,K=16 MMA with a K-major A operand costs ~150 cycles whatever N is (tensor pipe 21 %
   // active at N=64, 43 % at 128, 85 % at 256).  Cycling through kParts independent partial accumulators
   // (summed by the epilogue) was measured NOT to help (4 / 2 parts at BN = 64 / 128: 26.4 vs 25.9 ms per
@@ -115,7 +114,7 @@ __device__ __forceinline__ MnTile decode_mn(const TcDev& p, int tile) {
 // leader's commits multicast to empty[stage] / tfull[acc] of both CTAs; both CTAs' epilogue warps
 // arrive on the leader's tempty[acc].
 template <int BN, int MODE, int EPI, bool PAIR>
-__global__ void __launch_bounds__(PAIR ? kThreads : kThreads2, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
               const TcDev p) {
   using Cfg = TcCfg<BN>;
@@ -143,6 +142,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * S + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
   uint8_t* epi_stage = smem + S * Cfg::kStageBytes + 256;   // 16 KB, 128-byte aligned
+  float* epi_xchg = reinterpret_cast<float*>(epi_stage + 16384);   // 4 KB (GN only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -324,21 +324,12 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
   } else {
     // ============================= epilogue =================================
-    // Two groups of four epilogue warps (warps 2..5 and 6..9) take ALTERNATE tiles - group g owns accumulator
-    // buffer g - so two tiles' epilogues are in flight: a 128 x 256 tile's epilogue (tcgen05.ld -> staging ->
-    // coalesced stores, one dependent chain per warp) took ~15 K cycles, more than the MMA time of every layer
-    // with K <= 1152 (Upsample forward 45 % tensor-pipe activity).  CTA-pair kernels keep one group.
-    constexpr int NWG = PAIR ? 1 : 2;
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int wg = PAIR ? 0 : ((warp - 2) >> 2);
     const int row = q * 32 + lane;       // accumulator row owned by this thread
+    int acc = 0;
+    uint32_t acc_phase = 0;
     int gn_par = 0;
-    int it = -1;
     for (int tile = t_begin; tile < t_end; tile += t_step) {
-      ++it;
-      if (NWG == 2 && (it & 1) != wg) continue;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       int nt;
       bool valid;
       long long obase, rbase = 0;
@@ -385,8 +376,8 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       if (!A_MN && !p.out_f32 && !p.out_atomic) {
         // bf16 output: stage through shared memory so global stores / side-input loads are coalesced
         EpiArgs ea{p.out, p.bias, p.rowvec, p.res, p.Ncols, p.alpha, p.gn_ab, p.gn_ws, p.N, p.ws_ld};
-        epilogue_bf16_coalesced<BN, EPI, Cfg::kParts>(ea, epi_stage + (wg * 4 + q) * 4096, t_addr, lane, nt * BN,
-                                         valid && has_acc, obase, rbase, img, wait_acc, q, nullptr, &gn_par,
+        epilogue_bf16_coalesced<BN, EPI, Cfg::kParts>(ea, epi_stage + q * 4096, t_addr, lane, nt * BN, valid && has_acc,
+                                         obase, rbase, img, wait_acc, q, epi_xchg, &gn_par,
                                          EPI != EPI_PLAIN ? tile % p.gn_slots : 0);
       } else {
       wait_acc();
@@ -460,6 +451,7 @@ fdx_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
       if (lane == 0) {
         if constexpr (PAIR) mbar_arrive_cluster(&tempty[acc], 0); else mbar_arrive(&tempty[acc]);
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -484,7 +476,7 @@ int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcDev& d, cud
   int grid = fdx_num_sms();
   if (grid <= 0) return FDX_ERR_NO_DEVICE;
   if (d.ntiles < grid) grid = d.ntiles;
-  fdx_tc_kernel<BN, MODE, EPI, false><<<grid, kThreads2, Cfg::kSmemBytes, stream>>>(mA, mB, d);
+  fdx_tc_kernel<BN, MODE, EPI, false><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(mA, mB, d);
   fdx_note_kernel(FDX_KERNEL_TC);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
