@@ -322,7 +322,12 @@ def profile_kernels(trainer, images, noise, t, ctx=None):
         q, kk, heads, scale = a[0], a[1], a[6], a[8]
         return 8.0 * q.shape[0] * heads * q.shape[1] * kk.shape[1] * round(scale ** -2)
 
-    table = {"conv3x3_fwd": f_fwd, "conv3x3_dgrad": f_dgrad, "conv3x3_wgrad": f_wgrad, "gemm": f_gemm,
+    def f_1x1(a, k):         # x / dy (NHWC), w [.., Cin, Cout]: 1x1 convolution in conv geometry (fwd and dgrad)
+        x, wgt = a[0], a[1]
+        return 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * wgt.shape[-2] * wgt.shape[-1]
+
+    table = {"conv3x3_fwd": f_fwd, "conv3x3_dgrad": f_dgrad, "conv3x3_dgrad_gn": f_dgrad, "conv3x3_wgrad": f_wgrad,
+             "conv1x1_fwd": f_1x1, "conv1x1_dgrad": f_1x1, "gemm": f_gemm,
              "upconv3x3_fwd": f_up_fwd, "upconv3x3_dgrad": f_up_dgrad, "upconv3x3_wgrad": f_wgrad,
              "attention_fwd": f_attn_fwd, "attention_bwd": f_attn_bwd}
     orig = {n: getattr(ops, n) for n in table}
