@@ -86,16 +86,45 @@ template <bool SILU>
 __global__ void __launch_bounds__(kNT)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, long long xps, int HW, int C, int G,
                 const float* __restrict__ stats, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, long long yps) {
+                const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, long long yps,
+                const float* __restrict__ cols, int slots, int ld, int c0, float* __restrict__ stats_out) {
   const int vpp = C >> 3, rows = kNT / vpp, cpg = C / G;
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
+  // cols != nullptr: the statistics come straight from the producers' epilogue column sums
+  // ([slots][N][2][ld], channels c0 .. c0+C) - every CTA reduces its image's groups itself (one warp per group)
+  // instead of a separate stats_from_cols launch; the first CTA of the image stores them for the backward.
+  __shared__ float sg[2 * 64];
+  if (cols) {
+    const int N = gridDim.y;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int g = warp; g < G; g += kNT / 32) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int sl = 0; sl < slots; ++sl) {
+        const float* b = cols + (((long long)sl * N + n) * 2) * ld + c0 + g * cpg;
+        for (int c = lane; c < cpg; c += 32) { s0 += b[c]; s1 += b[ld + c]; }
+      }
+      s0 = warp_sum(s0);
+      s1 = warp_sum(s1);
+      if (lane == 0) {
+        sg[2 * g] = s0;
+        sg[2 * g + 1] = s1;
+        if (blockIdx.x == 0) {
+          stats_out[(long long)n * 2 * G + 2 * g] = s0;
+          stats_out[(long long)n * 2 * G + 2 * g + 1] = s1;
+        }
+      }
+    }
+    __syncthreads();
+  }
   if (tid >= rows * vpp) return;
   const int cv = tid % vpp, r = tid / vpp;
   const int g = (cv * 8) / cpg;
   const float cnt = (float)HW * (float)cpg;
-  const float mean = stats[(long long)n * 2 * G + 2 * g] / cnt;
-  const float var = fmaxf(0.f, stats[(long long)n * 2 * G + 2 * g + 1] / cnt - mean * mean);
+  const float sum0 = cols ? sg[2 * g] : stats[(long long)n * 2 * G + 2 * g];
+  const float sum1 = cols ? sg[2 * g + 1] : stats[(long long)n * 2 * G + 2 * g + 1];
+  const float mean = sum0 / cnt;
+  const float var = fmaxf(0.f, sum1 / cnt - mean * mean);
   const float rstd = rsqrtf(var + eps);
   const float sc = SILU ? 0.5f : 1.f;
   f32x2_t a[4], b[4];
@@ -1218,6 +1247,27 @@ int fdx_groupnorm_stats_from_cols(const float* cols, int slots, int N, int ld, i
   return FDX_OK;
 }
 
+int fdx_groupnorm_apply_cols(const fdx_act* x, int groups, const float* cols, int slots, int ld, int c0,
+                             const float* gamma, const float* beta, float eps, int silu, const fdx_act* y,
+                             float* stats_out, void* stream) {
+  int s = gn_check(x, groups, "groupnorm_apply_cols");
+  if (s != FDX_OK) return s;
+  FDX_REQUIRE(y && y->ptr && y->n == x->n && y->h == x->h && y->w == x->w && y->c == x->c,
+              "groupnorm_apply_cols: output shape mismatch");
+  FDX_REQUIRE(cols && stats_out && slots > 0 && c0 >= 0 && c0 + x->c <= ld && groups <= 64,
+              "groupnorm_apply_cols: bad column-sum workspace");
+  if (silu)
+    gn_apply_kernel<true><<<gn_grid(x, kU, 5), kNT, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x->ptr, x->pix_stride, x->h * x->w, x->c, groups, nullptr, gamma, beta, eps,
+        (__nv_bfloat16*)y->ptr, y->pix_stride, cols, slots, ld, c0, stats_out);
+  else
+    gn_apply_kernel<false><<<gn_grid(x, kU, 5), kNT, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x->ptr, x->pix_stride, x->h * x->w, x->c, groups, nullptr, gamma, beta, eps,
+        (__nv_bfloat16*)y->ptr, y->pix_stride, cols, slots, ld, c0, stats_out);
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
 int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const float* gamma,
                         const float* beta, float eps, int silu, const fdx_act* y, void* stream) {
   int s = gn_check(x, groups, "groupnorm_apply");
@@ -1227,11 +1277,11 @@ int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const 
   if (silu)
     gn_apply_kernel<true><<<gn_grid(x, kU, 5), kNT, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x->ptr, x->pix_stride, x->h * x->w, x->c, groups, stats, gamma, beta, eps,
-        (__nv_bfloat16*)y->ptr, y->pix_stride);
+        (__nv_bfloat16*)y->ptr, y->pix_stride, nullptr, 0, 0, 0, nullptr);
   else
     gn_apply_kernel<false><<<gn_grid(x, kU, 5), kNT, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x->ptr, x->pix_stride, x->h * x->w, x->c, groups, stats, gamma, beta, eps,
-        (__nv_bfloat16*)y->ptr, y->pix_stride);
+        (__nv_bfloat16*)y->ptr, y->pix_stride, nullptr, 0, 0, 0, nullptr);
   FDX_LAUNCH_CHECK();
   return FDX_OK;
 }

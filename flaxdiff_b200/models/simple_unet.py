@@ -55,6 +55,7 @@ def _attn_width(d: int) -> int:
 # engine got eight epilogue warps they beat the flat GEMM launch on the HBM-bound shapes
 # (profiles/layers_r02_res1x1.txt); FDX_RES1X1_GEMM=1 restores the flat launch.
 _RES1X1_GEMM = bool(os.environ.get("FDX_RES1X1_GEMM"))
+_GN_APPLY_V1 = bool(os.environ.get("FDX_GN_APPLY_V1"))
 
 class _SideStream:
     """Weight-gradient kernels have no consumer before the optimizer step, so the backward pass issues them
@@ -121,6 +122,17 @@ class Node:
         if done and root.cs is not None:
             return ops.groupnorm_stats_from_cols(root.cs, groups, self.coff, self.t.shape[-1])
         return ops.groupnorm_stats(self.t, groups)
+
+    def norm_apply(self, groups: int, gamma, beta, eps: float, silu: bool):
+        """(GroupNorm(+SiLU) of this tensor, its statistics): ONE launch when the producers' epilogues left the
+        column sums (fdx_groupnorm_apply_cols), else statistics (from columns or by their own pass) + apply.
+        FDX_GN_APPLY_V1=1 keeps the separate stats_from_cols launch."""
+        done = all(k.cs_ok for k in self.kids) if self.kids else self.cs_ok
+        root = self.parent if self.parent is not None else self
+        if done and root.cs is not None and groups <= 64 and not _GN_APPLY_V1:
+            return ops.groupnorm_apply_cols(self.t, groups, root.cs, self.coff, gamma, beta, eps, silu)
+        st = self.stats(groups)
+        return ops.groupnorm_apply(self.t, groups, st, gamma, beta, eps, silu), st
 
     def grad_buf(self) -> torch.Tensor:
         if self.g is None:
@@ -500,9 +512,7 @@ class Unet:
                 tape.append(("conv", name, cur, dst))
                 cur = dst
             elif kind == "out":
-                st = cur.stats(G)
-                a = ops.groupnorm_apply(cur.t, G, st, W[self._nout + "/scale"], W[self._nout + "/bias"],
-                                        OUT_EPS, True)
+                a, st = cur.norm_apply(G, W[self._nout + "/scale"], W[self._nout + "/bias"], OUT_EPS, True)
                 Fo = ops.conv_out_fwd(a, W[name + "/conv/kernel"], W[name + "/conv/bias"])
                 tape.append(("out", name, cur, st, a))
                 cur = None
@@ -514,8 +524,7 @@ class Unet:
     def _res_fwd(self, name, xin: Node, dst: Node, emb16, W, W16, G, eps):
         x = xin.t
         cin, cout = x.shape[-1], dst.t.shape[-1]
-        st1 = xin.stats(G)
-        a1 = ops.groupnorm_apply(x, G, st1, W[f"{name}/{self._n1}/scale"], W[f"{name}/{self._n1}/bias"], eps, True)
+        a1, st1 = xin.norm_apply(G, W[f"{name}/{self._n1}/scale"], W[f"{name}/{self._n1}/bias"], eps, True)
         pre = self._rows.pop(name, None)
         if pre is not None:                       # computed on the side stream at the start of the forward
             row, ev = pre
@@ -527,8 +536,7 @@ class Unet:
         hnode = Node(torch.empty((x.shape[0], x.shape[1], x.shape[2], cout), dtype=BF16, device=x.device))
         hmid = ops.conv3x3_fwd(a1, W16[f"{name}/conv1/conv/kernel"], W[f"{name}/conv1/conv/bias"], rowvec=row,
                                out=hnode.t, colstats=hnode.colstats())
-        st2 = hnode.stats(G)
-        a2 = ops.groupnorm_apply(hmid, G, st2, W[f"{name}/{self._n2}/scale"], W[f"{name}/{self._n2}/bias"], eps, True)
+        a2, st2 = hnode.norm_apply(G, W[f"{name}/{self._n2}/scale"], W[f"{name}/{self._n2}/bias"], eps, True)
         if cin != cout:
             Bn, hh, ww, _ = x.shape
             r = torch.empty((Bn, hh, ww, cout), dtype=BF16, device=x.device)

@@ -166,6 +166,20 @@ def groupnorm_apply(x, groups, stats, gamma, beta, eps: float, silu: bool, out=N
     return out
 
 
+def groupnorm_apply_cols(x, groups, cs: "ColStats", c0: int, gamma, beta, eps: float, silu: bool, out=None):
+    """groupnorm_apply with the statistics read from the producers' epilogue column sums (no stats_from_cols
+    launch) -> (y, stats[N][groups][2] for the backward)."""
+    if out is None:
+        out = torch.empty(tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((cs.n, groups, 2), dtype=torch.float32, device=x.device)
+    check(load().fdx_groupnorm_apply_cols(ctypes.byref(act(x, "x")), ctypes.c_int(groups), ptr(cs.ws),
+                                          ctypes.c_int(cs.slots), ctypes.c_int(cs.channels), ctypes.c_int(c0),
+                                          ptr(gamma), ptr(beta), ctypes.c_float(eps), ctypes.c_int(1 if silu else 0),
+                                          ctypes.byref(act(out, "out")), ptr(stats), stream_ptr()),
+          "groupnorm_apply_cols")
+    return out, stats
+
+
 def groupnorm_bwd(x, dy, groups, stats, gamma, beta, eps, silu, dgamma, dbeta, dx,
                   accumulate: bool = False, csum_img=None, csum_tot=None, addend=None) -> torch.Tensor:
     """dx (+)= d/dx GroupNorm(+SiLU); `addend`: dx = d/dx + addend (another tensor of the same shape)."""

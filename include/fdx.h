@@ -133,6 +133,13 @@ int fdx_groupnorm_stats(const fdx_act* x, int groups, float* stats, void* stream
 /* y = silu?((x-mean)*rstd*gamma+beta) (models/common.py:286-288,310-312; simple_unet.py:209-210). */
 int fdx_groupnorm_apply(const fdx_act* x, int groups, const float* stats, const float* gamma,
                         const float* beta, float eps, int silu, const fdx_act* y, void* stream);
+/* fdx_groupnorm_apply with the statistics taken straight from the producers' epilogue column sums
+ * (cols = [slots][N][2][ld] as written by fdx_conv3x3_fwd_stats / fdx_upconv3x3_fwd_stats, channels c0 .. c0+C of
+ * the buffer): no fdx_groupnorm_stats_from_cols launch; stats_out[N][groups][2] receives the statistics for the
+ * backward. */
+int fdx_groupnorm_apply_cols(const fdx_act* x, int groups, const float* cols, int slots, int ld, int c0,
+                             const float* gamma, const float* beta, float eps, int silu, const fdx_act* y,
+                             float* stats_out, void* stream);
 /* Backward of the pair above.  ws: f32 scratch of 2*N*C + 2*N*groups floats.  dgamma/dbeta ACCUMULATED.
  * csum_img [n][c] / csum_tot [c] (NULL allowed; csum_tot needs csum_img): column sums over pixels of the
  * dx this call produces, written (not accumulated) - the timestep row-vector and conv-bias gradients. */

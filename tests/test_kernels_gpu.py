@@ -389,6 +389,11 @@ def test_conv_fwd_fused_groupnorm_statistics(case):
     st = ops.groupnorm_stats_from_cols(cs, 8, coff, cout)
     ref = ops.groupnorm_stats(y, 8)
     assert rel(st, ref) < 1e-5
+    # GroupNorm(+SiLU) straight from the column sums (fdx_groupnorm_apply_cols) = stats_from_cols + apply
+    gamma, beta = 1 + 0.2 * torch.randn(cout, device=dev), 0.2 * torch.randn(cout, device=dev)
+    a_ref = ops.groupnorm_apply(y, 8, st, gamma, beta, 1e-4, True)
+    a_one, st_one = ops.groupnorm_apply_cols(y, 8, cs, coff, gamma, beta, 1e-4, True)
+    assert rel(st_one, st) < 1e-6 and rel(a_one, a_ref) < 1e-3
     # the sub-pixel upsample convolution: four parity launches add up to the same sums
     wf = torch.randn(3, 3, cin, cout, device=dev) / math.sqrt(9 * cin)
     weff = ops.upconv3x3_pack(wf)
