@@ -49,3 +49,25 @@ def test_documents_name_existing_c_abi_symbols():
             assert any(d == sym or d.startswith(sym) for d in declared), f"{doc} names {sym}"
     counts = re.findall(r"(\d+)[- ]entry[- ]point", _read("README.md")) + re.findall(r"\| (\d+) `fdx_\*` entry points", _read("DESIGN.md"))
     assert counts and all(int(c) == len(declared) for c in counts), (counts, len(declared))
+
+
+def test_environment_switches_in_design_exist_in_the_code():
+    """Every FDX_* switch DESIGN.md documents is read somewhere in the product (or bench.py), and every switch
+    the product reads is documented."""
+    design = _read("DESIGN.md")
+    documented = set(re.findall(r"`(FDX_[A-Z0-9_]+)(?:=[^`]*)?`", design))
+    code = ""
+    for base, _, files in os.walk(os.path.join(ROOT, "flaxdiff_b200")):
+        if os.sep + "build" in base or os.sep + "lib" in base:
+            continue
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh")):
+                code += _read(os.path.relpath(os.path.join(base, fn), ROOT))
+    code += _read("bench.py")
+    read_in_code = set(re.findall(r"getenv\(\"(FDX_[A-Z0-9_]+)\"\)", code)) | \
+        set(re.findall(r"environ(?:\.get)?[\(\[]\"(FDX_[A-Z0-9_]+)\"", code))
+    not_switches = {"FDX_OK", "FDX_BIND"}
+    missing = {v for v in documented - not_switches if v not in code}
+    assert not missing, f"DESIGN.md documents switches the code never reads: {sorted(missing)}"
+    undocumented = {v for v in read_in_code if v not in design}
+    assert not undocumented, f"switches read by the code but absent from DESIGN.md: {sorted(undocumented)}"
