@@ -2,8 +2,9 @@
 
 Only the contract the samplers / trainer need is kept: which batch key feeds which model
 kwarg, the cached unconditional ("null") embedding, and the per-sample null mixing used for
-classifier-free-guidance training.  The CLIP text encoder itself is out of scope (BASELINE
-config 4 uses frozen random text embeddings): `RandomEmbeddingEncoder` stands in for it.
+classifier-free-guidance training.  `CLIPTextEncoder` is the reference's text tower on the torch backend of
+`transformers` (weights must be in the local cache); BASELINE config 4 uses frozen random text embeddings:
+`RandomEmbeddingEncoder`.
 """
 from __future__ import annotations
 
@@ -52,6 +53,66 @@ class RandomEmbeddingEncoder(ConditioningEncoder):
 
     def serialize(self):
         return {"seq_len": self.seq_len, "features": self.features, "seed": self.seed}
+
+
+class CLIPTextEncoder(ConditioningEncoder):
+    """`CLIPTextEncoder` of the reference (flaxdiff/inputs/encoders.py:53-94) on the torch backend of
+    `transformers` (SURVEY $8 f3): tokenizer(padding="max_length", max_length=model_max_length, truncation=True)
+    -> CLIPTextModel -> last_hidden_state (B, 77, 768), frozen, evaluated under no_grad.  The text tower is
+    conditioning PRE-processing, not the hot path: it runs as stock PyTorch modules; its output feeds the UNet's
+    cross-attention as a bf16 CUDA tensor.  `model` / `tokenizer` may be injected (tests, custom towers);
+    `from_modelname` needs the weights in the local Hugging Face cache (there is no network here)."""
+    key = "text"
+
+    def __init__(self, model, tokenizer, modelname: str = "openai/clip-vit-large-patch14", backend: str = "torch",
+                 device=None, dtype: torch.dtype = torch.bfloat16):
+        self.model, self.tokenizer, self.modelname, self.backend = model, tokenizer, modelname, backend
+        self.device, self.dtype = device, dtype
+        if hasattr(model, "eval"):
+            model.eval()
+        if device is not None and hasattr(model, "to"):
+            model.to(device)
+
+    @staticmethod
+    def from_modelname(modelname: str = "openai/clip-vit-large-patch14", backend: str = "torch", device=None):
+        from .._lib import FdxError
+        if backend not in ("torch", "pt"):
+            raise FdxError(f"CLIPTextEncoder backend {backend!r}: only the torch backend exists here (JAX is not installed)")
+        try:
+            from transformers import AutoTokenizer, CLIPTextModel
+            model = CLIPTextModel.from_pretrained(modelname, local_files_only=True)
+            tokenizer = AutoTokenizer.from_pretrained(modelname, local_files_only=True)
+        except Exception as e:  # noqa: BLE001
+            raise FdxError(f"CLIPTextEncoder: cannot load {modelname!r} from the local Hugging Face cache "
+                           f"({type(e).__name__}); pass model= / tokenizer= or use RandomEmbeddingEncoder") from e
+        return CLIPTextEncoder(model, tokenizer, modelname, "torch", device)
+
+    def tokenize(self, data):
+        return self.tokenizer(list(data), padding="max_length", max_length=self.tokenizer.model_max_length,
+                              truncation=True, return_tensors="pt")
+
+    def encode_from_tokens(self, tokens) -> torch.Tensor:
+        ids, mask = tokens["input_ids"], tokens["attention_mask"]
+        if self.device is not None:
+            ids, mask = ids.to(self.device), mask.to(self.device)
+        with torch.no_grad():
+            out = self.model(input_ids=ids, attention_mask=mask).last_hidden_state
+        return out.to(self.dtype)
+
+    def __call__(self, data) -> torch.Tensor:
+        if isinstance(data, torch.Tensor):          # already embedded
+            return data
+        return self.encode_from_tokens(self.tokenize(data))
+
+    def serialize(self) -> dict:
+        return {"modelname": self.modelname, "backend": self.backend}
+
+    @staticmethod
+    def deserialize(serialized_config: dict):
+        return CLIPTextEncoder.from_modelname(serialized_config["modelname"], serialized_config.get("backend", "torch"))
+
+
+CONDITIONAL_ENCODERS_REGISTRY = {"text": CLIPTextEncoder}
 
 
 @dataclass
