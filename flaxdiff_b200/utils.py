@@ -142,3 +142,87 @@ DTYPE_MAP = {
 }
 PRECISION_MAP = {k: k for k in ('high', 'HIGH', 'default', 'DEFAULT', 'highest', 'HIGHEST', 'None', None)}
 ACTIVATION_MAP = {'swish': 'swish', 'silu': 'swish', 'jax._src.nn.functions.silu': 'swish'}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# configuration / checkpoint helpers of flaxdiff/utils.py:40-90, 239-263 (host side, no device work)
+# ---------------------------------------------------------------------------------------------------------
+DTYPE_MAP = {"bfloat16": torch.bfloat16, "float32": torch.float32, "float16": torch.float16, "None": None, None: None}
+# jax.lax.Precision names of the reference's configs: there is one matmul precision here (bf16 operands, f32
+# accumulation), so they all map to None ("backend default")
+PRECISION_MAP = {"high": None, "HIGH": None, "default": None, "DEFAULT": None, "highest": None, "HIGHEST": None,
+                 "None": None, None: None}
+# the reference maps names to jax.nn functions; the Unet here takes the NAME (only swish / silu is implemented)
+ACTIVATION_MAP = {"swish": "swish", "silu": "swish", "relu": "relu", "gelu": "gelu", "mish": "mish"}
+
+
+def map_nested_config(config: dict) -> dict:
+    """flaxdiff/utils.py:40-58: turn the strings of a serialised (wandb) model config back into objects - dtype
+    names into torch dtypes, precision names into None, activation names into the activation key, 'None' into
+    None; nested dicts recursively; other values are dropped exactly as the reference drops them."""
+    out = {}
+    for key, value in config.items():
+        if isinstance(value, dict):
+            out[key] = map_nested_config(value)
+        elif isinstance(value, str):
+            if value in DTYPE_MAP:
+                out[key] = DTYPE_MAP[value]
+            elif value in PRECISION_MAP:
+                out[key] = PRECISION_MAP[value]
+            elif value in ACTIVATION_MAP:
+                out[key] = ACTIVATION_MAP[value]
+            elif value == "None":
+                out[key] = None
+    return out
+
+
+def serialize_model(model) -> dict:
+    """flaxdiff/utils.py:60-82: the public attributes of a model object as a plain dict, callables (activation,
+    initialisers) and dtypes replaced by their names, nested dicts / lists of dicts handled recursively."""
+    def conv(v):
+        if isinstance(v, dict):
+            return {k: conv(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)):
+            return type(v)(conv(x) for x in v)
+        if isinstance(v, torch.dtype):
+            return str(v).split(".")[-1]
+        if callable(v):
+            return getattr(v, "__name__", str(v).split(".")[-1])
+        return v
+    return {k: conv(v) for k, v in vars(model).items() if not k.startswith("_")}
+
+
+def get_latest_checkpoint(checkpoint_path: str) -> str:
+    """flaxdiff/utils.py:84-90: the step directory with the largest number under `checkpoint_path`."""
+    import os
+    steps = sorted(int(d) for d in os.listdir(checkpoint_path) if d.isdigit())
+    if not steps:
+        raise FileNotFoundError(f"no step directories under {checkpoint_path}")
+    return os.path.join(checkpoint_path, str(steps[-1]))
+
+
+class AutoTextTokenizer:
+    """flaxdiff/utils.py:239-257: AutoTokenizer with CLIP's padding contract; returns input_ids, attention_mask and
+    the captions.  The tokenizer files must be in the local Hugging Face cache (no network here); a tokenizer
+    object may be passed instead."""
+
+    def __init__(self, tensor_type: str = "pt", modelname: str = "openai/clip-vit-large-patch14", tokenizer=None):
+        if tokenizer is None:
+            from transformers import AutoTokenizer
+            tokenizer = AutoTokenizer.from_pretrained(modelname, local_files_only=True)
+        self.tokenizer = tokenizer
+        self.tensor_type = tensor_type
+
+    def __call__(self, inputs):
+        tokens = self.tokenizer(inputs, padding="max_length", max_length=self.tokenizer.model_max_length,
+                                truncation=True, return_tensors=self.tensor_type)
+        return {"input_ids": tokens["input_ids"], "attention_mask": tokens["attention_mask"], "caption": inputs}
+
+    def __repr__(self):
+        return self.__class__.__name__ + "()"
+
+
+def defaultTextEncodeModel(modelname: str = "openai/clip-vit-large-patch14", backend: str = "torch"):
+    """flaxdiff/utils.py:261-263 (the torch backend is the only one here)."""
+    from .inputs import CLIPTextEncoder
+    return CLIPTextEncoder.from_modelname(modelname=modelname, backend=backend)
