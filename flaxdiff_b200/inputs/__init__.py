@@ -54,6 +54,12 @@ class RandomEmbeddingEncoder(ConditioningEncoder):
     def serialize(self):
         return {"seq_len": self.seq_len, "features": self.features, "seed": self.seed}
 
+    @staticmethod
+    def deserialize(serialized_config: dict):
+        return RandomEmbeddingEncoder(seq_len=serialized_config.get("seq_len", 77),
+                                      features=serialized_config.get("features", 768),
+                                      seed=serialized_config.get("seed", 0))
+
 
 class CLIPTextEncoder(ConditioningEncoder):
     """`CLIPTextEncoder` of the reference (flaxdiff/inputs/encoders.py:53-94) on the torch backend of
@@ -142,6 +148,23 @@ class ConditionalInputConfig:
                 "unconditional_input": self.unconditional_input,
                 "model_key_override": self.model_key_override}
 
+    @staticmethod
+    def deserialize(serialized_config: dict, registry: Optional[Dict[str, Any]] = None):
+        """inputs/__init__.py:55-74: rebuild the encoder through the registry (`encoder_key` -> class with a
+        `deserialize`), then the config.  `registry` extends / overrides CONDITIONAL_ENCODERS_REGISTRY (e.g.
+        {"text": RandomEmbeddingEncoder} where the CLIP weights are not available)."""
+        reg = dict(CONDITIONAL_ENCODERS_REGISTRY)
+        reg.update(registry or {})
+        encoder_key = serialized_config["encoder_key"]
+        encoder_class = reg.get(encoder_key)
+        if encoder_class is None:
+            raise ValueError(f"Unknown encoder type: {encoder_key}")
+        encoder = encoder_class.deserialize(serialized_config["encoder"])
+        return ConditionalInputConfig(encoder=encoder,
+                                      conditioning_data_key=serialized_config.get("conditioning_data_key"),
+                                      unconditional_input=serialized_config.get("unconditional_input"),
+                                      model_key_override=serialized_config.get("model_key_override"))
+
 
 @dataclass
 class DiffusionInputConfig:
@@ -182,3 +205,11 @@ class DiffusionInputConfig:
     def serialize(self):
         return {"sample_data_key": self.sample_data_key, "sample_data_shape": self.sample_data_shape,
                 "conditions": [c.serialize() for c in self.conditions]}
+
+    @staticmethod
+    def deserialize(serialized_config: dict, registry: Optional[Dict[str, Any]] = None):
+        """inputs/__init__.py:157-173."""
+        return DiffusionInputConfig(
+            sample_data_key=serialized_config["sample_data_key"],
+            sample_data_shape=tuple(serialized_config["sample_data_shape"]),
+            conditions=[ConditionalInputConfig.deserialize(c, registry) for c in serialized_config["conditions"]])

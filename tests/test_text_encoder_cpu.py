@@ -59,3 +59,18 @@ def test_from_modelname_fails_loudly_offline():
         CLIPTextEncoder.from_modelname("openai/clip-vit-large-patch14")
     with pytest.raises(FdxError, match="only the torch backend"):
         CLIPTextEncoder.from_modelname(backend="jax")
+
+
+def test_input_config_serialize_deserialize_roundtrip():
+    from flaxdiff_b200.inputs import RandomEmbeddingEncoder
+    enc = RandomEmbeddingEncoder(seq_len=77, features=32, seed=5)
+    cfg = DiffusionInputConfig("image", (64, 64, 3), [ConditionalInputConfig(
+        encoder=enc, conditioning_data_key="caption", unconditional_input="", model_key_override="textcontext")])
+    ser = cfg.serialize()
+    back = DiffusionInputConfig.deserialize(ser, registry={"text": RandomEmbeddingEncoder})
+    assert back.sample_data_key == "image" and back.sample_data_shape == (64, 64, 3)
+    c = back.conditions[0]
+    assert (c.conditioning_data_key, c.unconditional_input, c.model_key_override) == ("caption", "", "textcontext")
+    assert torch.equal(c.encoder(["x y"]), enc(["x y"])) and back.serialize() == ser
+    with pytest.raises(ValueError, match="Unknown encoder type"):
+        ConditionalInputConfig.deserialize(dict(ser["conditions"][0], encoder_key="audio"))
