@@ -862,3 +862,38 @@ def _np_tree(fp: FlatParams) -> dict:
 
 
 DiffusionTrainer = GeneralDiffusionTrainer
+SimpleTrainState = TrainState          # flaxdiff/trainer/simple_trainer.py:73-75 (same fields here: step, params,
+                                       # opt state, dynamic scale; metrics live on the trainer)
+from ..inputs import ConditionalInputConfig  # noqa: E402,F401  (re-exported by flaxdiff/trainer/__init__.py)
+
+
+class Metrics:
+    """Host-side stand-in for the clu metrics collection of flaxdiff/trainer/simple_trainer.py:68-70: a running
+    average of the loss (`accuracy` is never filled by the diffusion trainers)."""
+
+    def __init__(self, total: float = 0.0, count: int = 0):
+        self.total, self.count = float(total), int(count)
+
+    @classmethod
+    def empty(cls) -> "Metrics":
+        return cls()
+
+    def single_from_model_output(self, loss, **_) -> "Metrics":
+        return Metrics(float(loss), 1)
+
+    def merge(self, other: "Metrics") -> "Metrics":
+        return Metrics(self.total + other.total, self.count + other.count)
+
+    def compute(self) -> dict:
+        return {"loss": self.total / self.count if self.count else float("nan")}
+
+
+class SimpleTrainer:
+    """flaxdiff/trainer/simple_trainer.py:114-: the reference's trainer for ARBITRARY flax modules and loss
+    functions (it differentiates them with jax.value_and_grad).  This engine has no autograd - the UNet's backward
+    is an explicit program over libfdx kernels - so only the diffusion trainers exist; constructing this class
+    says so instead of silently training something else."""
+
+    def __init__(self, *args, **kwargs):
+        raise FdxError("SimpleTrainer (generic model + loss_fn) is outside the supported hot path: this engine "
+                       "trains flaxdiff_b200.models.simple_unet.Unet through GeneralDiffusionTrainer / DiffusionTrainer")

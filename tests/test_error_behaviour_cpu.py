@@ -65,3 +65,20 @@ def test_sampler_rejects_video_and_raw_conditioning():
         smp.generate_samples(None, 1, 16, sequence_length=8)
     with pytest.raises(FdxError, match="conditioning"):
         smp.generate_samples(None, 1, 16, conditioning=["a photo"])
+
+
+def test_trainer_namespace_matches_reference_exports():
+    """flaxdiff/trainer/__init__.py exports SimpleTrainer, SimpleTrainState, Metrics, DiffusionTrainer, TrainState,
+    GeneralDiffusionTrainer, ConditionalInputConfig; the generic SimpleTrainer refuses loudly."""
+    import pytest
+    from flaxdiff_b200 import trainer as T
+    from flaxdiff_b200._lib import FdxError
+    for name in ("SimpleTrainer", "SimpleTrainState", "Metrics", "DiffusionTrainer", "TrainState",
+                 "GeneralDiffusionTrainer", "ConditionalInputConfig"):
+        assert hasattr(T, name), name
+    with pytest.raises(FdxError, match="outside the supported hot path"):
+        T.SimpleTrainer(None, None)
+    m = T.Metrics.empty()
+    for v in (1.0, 2.0, 6.0):
+        m = m.merge(m.single_from_model_output(loss=v))
+    assert m.compute() == {"loss": 3.0}
